@@ -1,0 +1,293 @@
+"""-m gpu parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances (BASELINE.json north_star): symbols bit-exact except at round-half boundaries
+(mismatch rate <= 1e-5), reconstruction within 1e-3 max-abs on the 0..255 scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import codec_oracle as O
+import tf_image_compression_b200 as T
+from tf_image_compression_b200 import variants as V
+from gpu_common import MEAN, STD, make_codec, params_for, patches_from_images, rel_err
+
+pytestmark = pytest.mark.gpu
+
+MODES = os.environ.get("TIC_TEST_MODES", "fp32").split(",")
+
+# (variant, patch size, patches) — every BASELINE.json config plus the free table-driven variants
+LAYER_CASES = [("model_0", 128, 3), ("model_1", 256, 1), ("base_model/input_256", 256, 1), ("base_model/ch_128", 128, 2),
+               ("base_model/reduced_btn_32", 128, 2), ("model_3", 128, 2), ("model_2", 128, 2)]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("variant,P,n", LAYER_CASES)
+def test_layer_by_layer_activations(variant, P, n, mode):
+    """Every intermediate activation of encoder and decoder (what sess.run on the op would fetch)."""
+    codec, enc, dec = make_codec(variant, "fanin", compute=mode)
+    rs = np.random.RandomState(7)
+    x = rs.standard_normal((n, P, P, 3)).astype(np.float32)
+    worst = []
+    for graph, table, params, cin, x0 in (("encoder", O.VARIANTS[variant]["enc"], enc, 3, x), ("decoder", O.VARIANTS[variant]["dec"], dec, O.VARIANTS[variant]["bottleneck"], None)):
+        if x0 is None:
+            hb = codec.bottleneck_shape(P)[0]
+            x0 = (rs.standard_normal((n, hb, hb, cin)) * 3).astype(np.float32)
+        taps = []
+        O.run_layers(x0, table, cin, params, taps=taps)
+        prim = O.expand_layers(table, cin)
+        for k, (scope, ref) in enumerate(taps, start=1):
+            if prim[k - 1]["res_begin"]:
+                continue  # cannot stop inside a residual block
+            got = codec.run_layers(graph, x0, k)
+            assert got.shape == ref.shape, (scope, got.shape, ref.shape)
+            e = rel_err(got, ref)
+            worst.append((e, graph, scope))
+            assert e < 2e-5, f"{variant} {graph} layer {k} ({scope}): rel err {e:.3e}"
+    print(f"[{variant}@{P} {mode}] worst layer rel err: {max(worst)}")
+    codec.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("scheme", ["fanin", "reference"])
+def test_model0_symbols_match_oracle(scheme, mode):
+    """cfg1-shaped: model_0 @128; 96 patches = 393 216 symbols."""
+    codec, enc, dec = make_codec("model_0", scheme, compute=mode)
+    patches = patches_from_images(4, 512, 768, 128)  # 4 x 24 patches
+    sym = codec.encode_patches(patches)
+    ref = O.encoder(patches.astype(np.float32), "model_0", enc, MEAN, STD, 2)
+    assert sym.shape == ref.shape == (96, 8, 8, 64) and sym.dtype == np.uint8
+    mism = np.flatnonzero(sym.reshape(-1) != ref.reshape(-1))
+    rate = mism.size / ref.size
+    l64 = O.encoder_logits(patches.astype(np.float32), "model_0", enc, MEAN, STD, dtype=torch.float64).reshape(-1)
+    scale = np.abs(l64).max()
+    print(f"[model_0 {scheme} {mode}] mismatches {mism.size}/{ref.size} = {rate:.2e}; logit scale {scale:.3e}")
+    # documented round-half boundary: a mismatch may only sit where the fp64 logit is within fp32
+    # noise of the sigmoid == 0.5 threshold (dead zone (0, ~1.2e-7] plus accumulation error)
+    if mism.size:
+        assert np.abs(l64[mism]).max() < 1.5e-7 + 4e-6 * scale, np.abs(l64[mism]).max()
+    if scheme == "fanin":
+        assert rate <= 1e-5
+    else:
+        assert rate <= 5e-3  # 0.18 % of reference-init logits sit inside the dead zone
+    # f32 output (what sess.run returned) carries the same integers
+    symf = codec.encode_patches(patches, out_dtype=np.float32)
+    assert symf.dtype == np.float32 and np.array_equal(symf, sym.astype(np.float32))
+    codec.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("variant,P,n", [("model_0", 128, 24), ("model_1", 256, 4), ("base_model/input_256", 256, 3),
+                                         ("base_model/ch_128", 128, 6), ("base_model/ch_128", 256, 2),
+                                         ("base_model/reduced_btn_32", 128, 8), ("model_3", 128, 6), ("model_2", 128, 6)])
+def test_encode_decode_every_config(variant, P, n, mode):
+    codec, enc, dec = make_codec(variant, "fanin", compute=mode)
+    patches = patches_from_images(1, P, P * n, P, seed=11)
+    assert patches.shape[0] == n
+    sym = codec.encode_patches(patches)
+    ref = O.encoder(patches.astype(np.float32), variant, enc, MEAN, STD, 2)
+    nm = int((sym != ref).sum())
+    assert sym.shape == ref.shape
+    assert nm <= max(1, int(2e-5 * ref.size)), f"{variant}: {nm}/{ref.size} symbol mismatches"
+    rec = codec.decode_patches(ref)
+    rref = O.decoder(ref, variant, dec, MEAN, STD, 2)
+    assert rec.shape == rref.shape == (n, P, P, 3)
+    err = float(np.abs(rec - rref).max())
+    print(f"[{variant}@{P} {mode}] symbol mismatches {nm}/{ref.size}; recon max-abs err {err:.3e}")
+    assert err <= 1e-3
+    codec.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_reference_init_reconstruction(mode):
+    codec, enc, dec = make_codec("model_0", "reference", compute=mode)
+    sym = np.random.RandomState(3).randint(0, 2, size=(24, 8, 8, 64)).astype(np.uint8)
+    rec = codec.decode_patches(sym)
+    rref = O.decoder(sym, "model_0", dec, MEAN, STD, 2)
+    assert float(np.abs(rec - rref).max()) <= 1e-3
+    codec.close()
+
+
+def test_fused_crop_and_stitch_equal_the_host_helpers():
+    """encode_images == encoder(crop_image_input_patches(...)); decode_images == around(concat_patches(decoder))."""
+    codec, enc, dec = make_codec("model_0", "fanin")
+    for (h, w) in [(512, 768), (300, 200), (129, 385)]:
+        imgs = np.stack([O.synthetic_image(h, w, 20 + i) for i in range(3)])
+        sym_i = codec.encode_images(imgs, 128)
+        gh, gw = -(-h // 128), -(-w // 128)
+        assert sym_i.shape == (3, gh * gw, 8, 8, 64)
+        for i in range(3):
+            patches = np.stack(T.utils.crop_image_input_patches(imgs[i], 128))
+            assert np.array_equal(codec.encode_patches(patches), sym_i[i]), (h, w, i)
+        rec_u8 = codec.decode_images(sym_i, h, w, 128)
+        rec_f = codec.decode_images(sym_i, h, w, 128, out_dtype=np.float32)
+        assert rec_u8.shape == (3, h, w, 3) and rec_u8.dtype == np.uint8
+        for i in range(3):
+            p = codec.decode_patches(sym_i[i])
+            full = T.utils.concat_patches(list(p), h, w, 128)
+            assert np.array_equal(full, rec_f[i])
+            assert np.array_equal(np.around(full).astype(np.uint8), rec_u8[i])
+        assert np.array_equal(codec.round_u8(rec_f), rec_u8)
+    # oracle end to end on one image (encode.py:153-182 + decode.py:204-249 without the entropy coder)
+    img = O.synthetic_image(300, 200, 99)
+    s_ref, r_ref = O.codec_roundtrip(img, "model_0", enc, dec, MEAN, STD, 2, 128)
+    s = codec.encode_images(img[None], 128)[0]
+    assert (s != s_ref).sum() <= 1
+    r = codec.decode_images(s_ref[None], 300, 200, 128)[0]
+    assert np.abs(r.astype(int) - r_ref.astype(int)).max() <= 1 and (r != r_ref).mean() < 1e-4
+    codec.close()
+
+
+def test_histogram_and_position_sums_are_exact():
+    codec, enc, dec = make_codec("base_model/reduced_btn_32", "fanin")
+    patches = patches_from_images(2, 256, 384, 128, seed=5)
+    codec.hist_reset()
+    sym = codec.encode_patches(patches)
+    counts = codec.hist_read()
+    assert counts.dtype == np.uint64
+    assert np.array_equal(counts, np.bincount(sym.reshape(-1), minlength=2))
+    assert np.array_equal(counts.astype(np.float64), O.symbol_histogram(sym, 2))
+    sym2 = codec.encode_patches(patches[:5])  # accumulates (get_encoded_distribution.py:126)
+    assert np.array_equal(codec.hist_read(), counts + np.bincount(sym2.reshape(-1), minlength=2).astype(np.uint64))
+    sums = codec.position_sums(sym)
+    assert np.array_equal(sums, sym.reshape(sym.shape[0], -1).sum(0).astype(np.uint64))
+    mean, _, _ = O.position_mean([sym])
+    np.testing.assert_allclose(sums / sym.shape[0], mean, atol=1e-12)
+    codec.close()
+
+
+def test_quan_scale_256():
+    codec, enc, dec = make_codec("model_0", "fanin", q=256)
+    patches = patches_from_images(1, 256, 256, 128, seed=8)
+    codec.hist_reset()
+    sym = codec.encode_patches(patches)
+    ref = O.encoder(patches.astype(np.float32), "model_0", enc, MEAN, STD, 256)
+    d = np.abs(sym.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-3
+    assert np.array_equal(codec.hist_read(), np.bincount(sym.reshape(-1), minlength=256))
+    rec = codec.decode_patches(ref)
+    rref = O.decoder(ref, "model_0", dec, MEAN, STD, 256)
+    assert float(np.abs(rec - rref).max()) <= 1e-3
+    codec.close()
+
+
+def test_postfilter_and_rmbe_match_oracle():
+    codec, enc, dec = make_codec("model_1", "fanin")
+    pp = O.init_params(O.POSTFILTERS["rmbe"], 3, 77, "fanin")
+    pm, ps = np.array([110.0, 108.0, 99.0], np.float32), np.array([55.0, 57.0, 60.0], np.float32)
+    codec.set_postfilter(pp, pm, ps)
+    tiles = patches_from_images(1, 128, 384, 128, seed=31).astype(np.float32)
+    got = codec.postfilter_patches(tiles)
+    ref = O.postfilter(tiles, "rmbe", pp, pm, ps)
+    assert float(np.abs(got - ref).max()) <= 1e-3
+    imgs = np.stack([O.synthetic_image(384, 448, 40 + i).astype(np.float32) for i in range(2)])
+    want = np.stack([O.rmbe(im, lambda t: O.postfilter(t, "rmbe", pp, pm, ps)) for im in imgs])
+    work = imgs.copy()
+    codec.postfilter_images(work)
+    assert float(np.abs(work - want).max()) <= 2e-3  # two chained passes
+    # border strips are untouched (submit/2/rmbe/rmbe.py: first/last 64 px and remainders)
+    assert np.array_equal(work[:, :64, :64], imgs[:, :64, :64])
+    T.rmbe.bind(codec)
+    single = T.rmbe.rmbe(imgs[0].copy())
+    assert np.array_equal(single, work[0])
+    # alternative 4-layer post-filter (rm_block_effect/model_1/model.py:107-168)
+    pp1 = O.init_params(O.POSTFILTERS["rmbe_model_1"], 3, 78, "fanin")
+    codec.set_postfilter(pp1, pm, ps, name="rmbe_model_1")
+    got1 = codec.postfilter_patches(tiles[:2])
+    ref1 = O.postfilter(tiles[:2], "rmbe_model_1", pp1, pm, ps)
+    assert float(np.abs(got1 - ref1).max()) <= 1e-3
+    codec.close()
+
+
+def test_device_buffers_chunking_and_determinism():
+    codec, enc, dec = make_codec("model_0", "fanin")
+    patches = patches_from_images(2, 384, 512, 128, seed=50)  # 24 patches
+    base = codec.encode_patches(patches)
+    d_in = torch.from_numpy(patches).cuda()
+    d_out = codec.encode_patches(d_in)
+    assert d_out.is_cuda and np.array_equal(d_out.cpu().numpy(), base)
+    codec.set_chunk_patches(5)  # ragged chunks: 5,5,5,5,4
+    assert np.array_equal(codec.encode_patches(patches), base)
+    assert np.array_equal(codec.encode_patches(d_in).cpu().numpy(), base)
+    rec = codec.decode_patches(base)
+    codec.set_chunk_patches(7)
+    assert np.array_equal(codec.decode_patches(base), rec)
+    assert np.array_equal(codec.decode_patches(torch.from_numpy(base).cuda()).cpu().numpy(), rec)
+    # f32 patches give the same symbols as u8 patches (normalisation LUT == arithmetic)
+    assert np.array_equal(codec.encode_patches(patches.astype(np.float32)), base)
+    assert codec.launch_count > 0 and codec.last_kernel_ms() > 0
+    # empty batch
+    assert codec.encode_patches(np.zeros((0, 128, 128, 3), np.uint8)).shape == (0, 8, 8, 64)
+    codec.close()
+
+
+def test_reference_module_surface_and_errors():
+    codec, enc, dec = make_codec("model_0", "fanin")
+    model = T.ModelModule("model_0", codec)
+    patches = patches_from_images(1, 128, 256, 128, seed=60)
+    out = model.encoder(patches.astype(np.float32), 128, 2)  # float32 feed like encode.py:140,157
+    assert out.dtype == np.float32 and out.shape == (2, 8, 8, 64) and set(np.unique(out)) <= {0.0, 1.0}
+    seq = np.asarray(out).reshape(-1).astype(int).tolist()  # encode.py:175-182
+    assert len(seq) == 2 * 8 * 8 * 64
+    rec = model.decoder(out, 2)
+    assert rec.shape == (2, 128, 128, 3) and rec.min() >= 0 and rec.max() <= 255
+    with pytest.raises(ValueError):
+        model.decoder(out + 0.5, 2)
+    with pytest.raises(ValueError):
+        model.encoder(patches, 128, 3)
+    with pytest.raises(ValueError):
+        codec.encode_patches(np.zeros((2, 128, 64, 3), np.uint8))
+    with pytest.raises(ValueError):
+        codec.decode_patches(np.zeros((2, 8, 8, 32), np.uint8))
+    with pytest.raises(T.TicError):
+        codec.postfilter_patches(np.zeros((1, 128, 128, 3), np.float32))
+    with pytest.raises(KeyError):
+        T.Codec("model_0", enc_params={"encode_0/kernel": np.zeros((3, 3, 3, 32), np.float32)})
+    codec.close()
+
+
+def test_golden_fixture_cfg1():
+    """BASELINE config 1 (768x512 image, model_0, 128x128 patches) against the committed fixture
+    (tests/golden/make_golden.py)."""
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "cfg1_model0_768x512.npz")
+    ov = O.VARIANTS["model_0"]
+    enc = O.init_params(ov["enc"], 3, 1234, "fanin")
+    dec = O.init_params(ov["dec"], ov["bottleneck"], 1235, "fanin")
+    chk = [float(sum(np.float64(v).sum() for v in enc.values())), float(sum(np.float64(v).sum() for v in dec.values()))]
+    np.testing.assert_allclose(chk, z["weight_checksum"], rtol=0, atol=1e-9)
+    codec = T.Codec("model_0", quan_scale=2, mean=z["mean"], std=z["std"], enc_params=enc, dec_params=dec)
+    sym = codec.encode_images(z["image"][None], 128)[0]
+    assert sym.shape == (24, 8, 8, 64)
+    packed = np.packbits(sym.reshape(-1))
+    assert (np.unpackbits(packed ^ z["symbols_packed"]).sum()) <= 1
+    rec = codec.decode_images(np.unpackbits(z["symbols_packed"]).reshape(1, 24, 8, 8, 64), 512, 768, 128)[0]
+    d = np.abs(rec.astype(int) - z["recon"].astype(int))
+    assert d.max() <= 1 and (d != 0).mean() < 1e-4
+    codec.close()
+
+
+def test_full_size_properties_cfg2_shard():
+    """BASELINE config 2 at one GPU's 8-image share (8 x 2048x1536, 1 536 patches): size-independent
+    properties — determinism, batch == per-image, histogram == symbol count, decode idempotence."""
+    codec, enc, dec = make_codec("model_0", "fanin")
+    rs = np.random.RandomState(1234)
+    imgs = rs.randint(0, 256, size=(8, 1536, 2048, 3), dtype=np.uint8)
+    d_imgs = torch.from_numpy(imgs).cuda()
+    codec.hist_reset()
+    sym = codec.encode_images(d_imgs, 128)
+    assert tuple(sym.shape) == (8, 192, 8, 8, 64)
+    counts = codec.hist_read()
+    assert int(counts.sum()) == sym.numel() and int(counts[1]) == int(sym.sum())
+    assert torch.equal(codec.encode_images(d_imgs, 128), sym)  # deterministic
+    one = codec.encode_images(d_imgs[5:6].contiguous(), 128)
+    assert torch.equal(one[0], sym[5])  # batch == per image
+    host = codec.encode_images(imgs[:2], 128)  # host path == device path
+    assert np.array_equal(host, sym[:2].cpu().numpy())
+    rec = codec.decode_images(sym, 1536, 2048, 128)
+    assert tuple(rec.shape) == (8, 1536, 2048, 3) and rec.dtype == torch.uint8
+    assert torch.equal(codec.decode_images(sym, 1536, 2048, 128), rec)
+    # spot-check one patch of one image against the oracle
+    p = imgs[3, 128:256, 256:384][None].astype(np.float32)
+    assert (O.encoder(p, "model_0", enc, MEAN, STD, 2)[0] != sym[3, 1 * 16 + 2].cpu().numpy()).sum() <= 1
+    codec.close()

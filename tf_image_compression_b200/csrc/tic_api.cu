@@ -1,0 +1,1031 @@
+// C-ABI implementation (include/tic.h): handle, graph executor, chunked H2D -> compute -> D2H
+// pipeline, and kernel dispatch.  No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tic.h"
+#include "tic_simt.cuh"
+#include "tic_umma.cuh"
+
+using namespace tic;
+
+namespace {
+
+std::string g_create_error;
+
+struct Layer {
+  tic_layer_desc d{};
+  float* w = nullptr;     // device [9][cin][cout]
+  float* b = nullptr;     // device [cout]
+  UmmaWeights uw;         // tensor-path operand images (built lazily from w)
+  bool loaded = false;
+};
+
+struct Graph {
+  std::vector<Layer> layers;
+  float mean[3] = {0, 0, 0}, stdv[3] = {1, 1, 1};
+  bool has_norm = false;
+  float* d_normlut = nullptr;  // [3][256]
+};
+
+struct IoSpec {
+  int mode = IO_ACT;
+  const void* in = nullptr;
+  void* out = nullptr;
+  Geo geo{};
+};
+
+}  // namespace
+
+struct tic_codec {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[2]{}, ev_comp[2]{}, ev_out[2]{}, ev_t0 = nullptr, ev_t1 = nullptr;
+  Graph g[3];
+  int q = 0;
+  float* d_symlut = nullptr;  // [256]
+  unsigned long long* d_hist = nullptr;  // [256]
+  int mode = TIC_COMPUTE_FP32;
+  int chunk128 = 1024;
+  // workspaces
+  float* act[3] = {nullptr, nullptr, nullptr};
+  size_t act_bytes = 0;
+  void* stage_in[2] = {nullptr, nullptr};
+  void* stage_out[2] = {nullptr, nullptr};
+  size_t stage_in_bytes = 0, stage_out_bytes = 0;
+  int64_t launches = 0;
+  float last_ms = 0.f;
+  bool profile = false;
+  struct ProfRec {
+    int graph, layer;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<ProfRec> prof_pending;
+  std::vector<float> prof_ms[3];
+  std::vector<int64_t> prof_n[3];
+  int num_sms = 148;
+  std::string err;
+};
+
+namespace {
+
+int fail(tic_codec* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define TIC_CUDA(h, expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t e_ = (expr);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      return fail((h), TIC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// TF SAME: out = ceil(in / s); pad_total = max((out-1)*s + 3 - in, 0); before = total / 2
+void same_pad(int in, int s, int* out, int* before) {
+  *out = (in + s - 1) / s;
+  int total = std::max((*out - 1) * s + 3 - in, 0);
+  *before = total / 2;
+}
+
+// ---- SIMT launch planning -------------------------------------------------------------------
+template <int OCB, int S>
+int launch_conv_t(tic_codec* h, const LayerArgs& a, const SmemPlan& sp, dim3 grid, size_t smem) {
+  auto k = conv3x3_simt_kernel<OCB, S>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    TIC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k<<<grid, kThreads, smem, h->stream>>>(a, sp);
+  return TIC_OK;
+}
+template <int OCB>
+int launch_deconv_t(tic_codec* h, const LayerArgs& a, const SmemPlan& sp, dim3 grid, size_t smem) {
+  auto k = deconv3x3_simt_kernel<OCB>;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    TIC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  k<<<grid, kThreads, smem, h->stream>>>(a, sp);
+  return TIC_OK;
+}
+
+// Pick the row pitch so that the (up to four) row groups a warp spans land in distinct banks.
+int pick_pitch(int iw, int lanes_x, int row_words /* words between a warp's row groups, per pitch unit */, int s) {
+  if (lanes_x * s >= 32) return iw | 1;
+  for (int c = iw; c < iw + 32; ++c)
+    if ((row_words * c) % 32 == (lanes_x * s) % 32) return c;
+  return iw;
+}
+
+int launch_simt(tic_codec* h, LayerArgs a, int kind, int stride) {
+  SmemPlan sp{};
+  int ocb, grid_y;
+  if (kind == TIC_CONV) {
+    ocb = a.cout >= 64 ? 64 : a.cout > 16 ? 32 : a.cout > 8 ? 16 : 8;
+    const int ppc = 8192 / ocb;  // output pixels per CTA
+    a.TW = std::min(32, pow2ceil(a.wout));
+    a.TH = std::min(std::max(4, pow2ceil(a.hout)), ppc / a.TW);
+    a.TP = ppc / (a.TW * a.TH);
+    a.tiles_x = (a.wout + a.TW - 1) / a.TW;
+    a.tiles_y = (a.hout + a.TH - 1) / a.TH;
+    sp.ih = (a.TH - 1) * stride + 3;
+    sp.iw = (a.TW - 1) * stride + 3;
+    sp.iwp = pick_pitch(sp.iw, a.TW, 4 * stride, stride);
+  } else {
+    ocb = a.cout >= 32 ? 32 : a.cout > 8 ? 16 : a.cout > 4 ? 8 : 4;
+    const int ipc = 4096 / ocb;  // input pixels per CTA
+    a.TW = std::min(32, pow2ceil(a.win));
+    a.TH = std::min(std::max(4, pow2ceil(a.hin)), ipc / a.TW);
+    a.TP = ipc / (a.TW * a.TH);
+    a.tiles_x = (a.win + a.TW - 1) / a.TW;
+    a.tiles_y = (a.hin + a.TH - 1) / a.TH;
+    sp.ih = a.TH + 1;
+    sp.iw = a.TW + 1;
+    sp.iwp = pick_pitch(sp.iw, a.TW, 4, 1);
+  }
+  sp.cstr = sp.ih * sp.iwp;
+  sp.pstr = kIcc * sp.cstr;
+  {
+    // lanes of one warp may straddle patches: offset consecutive patches to fresh banks
+    const int lanes_per_patch = a.TW * a.TH / 4;
+    if (lanes_per_patch < 32 && a.TP > 1) {
+      const int want = (lanes_per_patch * (kind == TIC_CONV ? stride : 1)) % 32;
+      while (sp.pstr % 32 != want) ++sp.pstr;
+    }
+  }
+  grid_y = (a.cout + ocb - 1) / ocb;
+  const long long groups = (a.n + a.TP - 1) / a.TP;
+  const long long gx = (long long)a.tiles_x * a.tiles_y * groups;
+  if (gx <= 0 || gx > 0x7fffffffLL) return fail(h, TIC_ERR_INVALID, "grid too large (%lld)", gx);
+  dim3 grid((unsigned)gx, (unsigned)grid_y);
+  const size_t smem = ((size_t)a.TP * sp.pstr + 9 * kIcc * ocb) * sizeof(float);
+  if (smem > 200 * 1024) return fail(h, TIC_ERR_UNSUPPORTED, "tile needs %zu B shared memory", smem);
+  int rc = TIC_OK;
+  if (kind == TIC_CONV) {
+    if (stride == 1) {
+      switch (ocb) {
+        case 64: rc = launch_conv_t<64, 1>(h, a, sp, grid, smem); break;
+        case 32: rc = launch_conv_t<32, 1>(h, a, sp, grid, smem); break;
+        case 16: rc = launch_conv_t<16, 1>(h, a, sp, grid, smem); break;
+        default: rc = launch_conv_t<8, 1>(h, a, sp, grid, smem); break;
+      }
+    } else {
+      switch (ocb) {
+        case 64: rc = launch_conv_t<64, 2>(h, a, sp, grid, smem); break;
+        case 32: rc = launch_conv_t<32, 2>(h, a, sp, grid, smem); break;
+        case 16: rc = launch_conv_t<16, 2>(h, a, sp, grid, smem); break;
+        default: rc = launch_conv_t<8, 2>(h, a, sp, grid, smem); break;
+      }
+    }
+  } else {
+    switch (ocb) {
+      case 32: rc = launch_deconv_t<32>(h, a, sp, grid, smem); break;
+      case 16: rc = launch_deconv_t<16>(h, a, sp, grid, smem); break;
+      case 8: rc = launch_deconv_t<8>(h, a, sp, grid, smem); break;
+      default: rc = launch_deconv_t<4>(h, a, sp, grid, smem); break;
+    }
+  }
+  if (rc != TIC_OK) return rc;
+  h->launches++;
+  TIC_CUDA(h, cudaGetLastError());
+  return TIC_OK;
+}
+
+// ---- graph executor -------------------------------------------------------------------------
+struct Shape {
+  int h, w, c;
+};
+
+int graph_out_shape(const Graph& g, Shape in, Shape* out, size_t* max_act_elems, int limit = -1) {
+  Shape s = in;
+  size_t mx = 0;
+  const size_t L = limit > 0 ? std::min<size_t>((size_t)limit, g.layers.size()) : g.layers.size();
+  for (size_t i = 0; i < L; ++i) {
+    const tic_layer_desc& d = g.layers[i].d;
+    if (d.cin != s.c) return -1;
+    if (d.kind == TIC_CONV) {
+      int pb;
+      same_pad(s.h, d.stride, &s.h, &pb);
+      same_pad(s.w, d.stride, &s.w, &pb);
+    } else {
+      s.h *= 2;
+      s.w *= 2;
+    }
+    s.c = d.cout;
+    if (i + 1 < L) mx = std::max(mx, (size_t)s.h * s.w * s.c);
+  }
+  *out = s;
+  if (max_act_elems) *max_act_elems = mx;
+  return 0;
+}
+
+int check_graph_ready(tic_codec* h, int gi, bool need_norm) {
+  Graph& g = h->g[gi];
+  if (g.layers.empty()) return fail(h, TIC_ERR_STATE, "graph %d not configured (tic_set_graph)", gi);
+  for (size_t i = 0; i < g.layers.size(); ++i)
+    if (!g.layers[i].loaded) return fail(h, TIC_ERR_STATE, "graph %d layer %zu has no weights (tic_load_weights)", gi, i);
+  if (need_norm && !g.has_norm) return fail(h, TIC_ERR_STATE, "graph %d has no normalisation (tic_set_norm)", gi);
+  return TIC_OK;
+}
+
+// Run graph gi over n patches whose first-layer input map is h0 x w0 x c0.
+int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, int n, int h0, int w0, int limit = -1) {
+  Graph& g = h->g[gi];
+  const int L = limit > 0 ? std::min(limit, (int)g.layers.size()) : (int)g.layers.size();
+  Shape s{h0, w0, g.layers[0].d.cin};
+  size_t mx = 0;
+  Shape so;
+  if (graph_out_shape(g, s, &so, &mx, limit) != 0) return fail(h, TIC_ERR_INVALID, "layer channel chain is inconsistent");
+  const size_t need = mx * (size_t)n * sizeof(float);
+  if (need > h->act_bytes) {
+    TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 3; ++i) {
+      if (h->act[i]) cudaFree(h->act[i]);
+      h->act[i] = nullptr;
+    }
+    h->act_bytes = 0;
+    for (int i = 0; i < 3; ++i) {
+      cudaError_t e = cudaMalloc((void**)&h->act[i], need);
+      if (e != cudaSuccess) return fail(h, TIC_ERR_NOMEM, "cudaMalloc(%zu) for activations failed: %s", need, cudaGetErrorString(e));
+    }
+    h->act_bytes = need;
+  }
+  int cur = -1;            // buffer index holding the current activation (-1: caller input)
+  int res_buf = -1;        // buffer holding the residual source
+  for (int i = 0; i < L; ++i) {
+    Layer& ly = g.layers[i];
+    const tic_layer_desc& d = ly.d;
+    LayerArgs a{};
+    a.n = n;
+    a.hin = s.h;
+    a.win = s.w;
+    a.cin = s.c;
+    if (d.kind == TIC_CONV) {
+      same_pad(s.h, d.stride, &a.hout, &a.pad_t);
+      same_pad(s.w, d.stride, &a.wout, &a.pad_l);
+    } else {
+      a.hout = 2 * s.h;
+      a.wout = 2 * s.w;
+    }
+    a.cout = d.cout;
+    a.act = d.act;
+    a.wgt = ly.w;
+    a.bias = ly.b;
+    a.q = h->q;
+    a.hist = h->d_hist;
+    for (int c = 0; c < 3; ++c) {
+      a.mean[c] = g.mean[c];
+      a.stdv[c] = g.stdv[c];
+    }
+    // input
+    if (i == 0) {
+      a.in = io_in.in;
+      a.in_mode = io_in.mode;
+      a.geo = io_in.geo;
+      a.lut = (io_in.mode == IO_U8_NORM) ? g.d_normlut : (io_in.mode == IO_U8_SYMLUT ? h->d_symlut : nullptr);
+    } else {
+      a.in = h->act[cur];
+      a.in_mode = IO_ACT;
+    }
+    if (d.res_begin) res_buf = cur;
+    // output buffer: any workspace buffer that is neither the input nor the live residual
+    int ob = -1;
+    if (i == L - 1) {
+      a.out = io_out.out;
+      a.out_mode = io_out.mode;
+      if (i == 0) {
+        // single-layer graph: geo is shared by prologue and epilogue only if both need it
+        if (io_out.mode != IO_ACT) a.geo = io_out.geo;
+      } else {
+        a.geo = io_out.geo;
+      }
+    } else {
+      for (int b = 0; b < 3; ++b)
+        if (b != cur && b != res_buf) {
+          ob = b;
+          break;
+        }
+      a.out = h->act[ob];
+      a.out_mode = IO_ACT;
+    }
+    if (d.res_end) {
+      if (res_buf < 0) return fail(h, TIC_ERR_INVALID, "res_end without res_begin at layer %d", i);
+      a.res = h->act[res_buf];
+    }
+    int rc;
+    tic_codec::ProfRec pr{gi, i, nullptr, nullptr};
+    if (h->profile) {
+      cudaEventCreate(&pr.e0);
+      cudaEventCreate(&pr.e1);
+      cudaEventRecord(pr.e0, h->stream);
+    }
+    if (h->mode != TIC_COMPUTE_FP32 && umma_supported(a, d.kind, d.stride)) {
+      rc = launch_umma(h->stream, a, d.kind, d.stride, ly.w, &ly.uw, h->mode == TIC_COMPUTE_TENSOR_3XTF32,
+                       h->num_sms, &h->err);
+      if (rc == TIC_OK) h->launches++;
+    } else {
+      rc = launch_simt(h, a, d.kind, d.stride);
+    }
+    if (h->profile) {
+      cudaEventRecord(pr.e1, h->stream);
+      h->prof_pending.push_back(pr);
+    }
+    if (rc != TIC_OK) return rc;
+    if (d.res_end) res_buf = -1;
+    cur = ob;
+    s.h = a.hout;
+    s.w = a.wout;
+    s.c = a.cout;
+  }
+  return TIC_OK;
+}
+
+int patches_per_chunk(const tic_codec* h, int P) {
+  double scale = (128.0 / P) * (128.0 / P);
+  int c = (int)(h->chunk128 * scale);
+  return std::max(1, c);
+}
+
+// Generic chunked driver.  `units` are processed `upc` (units per chunk) at a time; a unit is a
+// patch or a whole image.  in_unit_bytes / out_unit_bytes describe the caller's buffers; run()
+// executes one chunk given device pointers (chunk-local when staged from host) and the unit offset.
+template <typename RunFn>
+int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64_t upc, size_t in_unit_bytes,
+          size_t out_unit_bytes, bool inout_same, RunFn run) {
+  if (units <= 0) return TIC_OK;
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
+  if (mem == TIC_MEM_DEVICE) {
+    for (int64_t u0 = 0; u0 < units; u0 += upc) {
+      int64_t nu = std::min<int64_t>(upc, units - u0);
+      int rc = run(in, out, u0, nu, /*local=*/false);
+      if (rc != TIC_OK) return rc;
+    }
+    TIC_CUDA(h, cudaEventRecord(h->ev_t1, h->stream));
+    return TIC_OK;
+  }
+  // host buffers: double-buffered staging, copies on side streams
+  const size_t in_need = (size_t)upc * in_unit_bytes, out_need = (size_t)upc * out_unit_bytes;
+  if (h->stage_in_bytes < in_need) {
+    for (int b = 0; b < 2; ++b) {
+      if (h->stage_in[b]) cudaFree(h->stage_in[b]);
+      h->stage_in[b] = nullptr;
+    }
+    h->stage_in_bytes = 0;
+    for (int b = 0; b < 2; ++b) TIC_CUDA(h, cudaMalloc(&h->stage_in[b], in_need));
+    h->stage_in_bytes = in_need;
+  }
+  if (!inout_same && h->stage_out_bytes < out_need) {
+    for (int b = 0; b < 2; ++b) {
+      if (h->stage_out[b]) cudaFree(h->stage_out[b]);
+      h->stage_out[b] = nullptr;
+    }
+    h->stage_out_bytes = 0;
+    for (int b = 0; b < 2; ++b) TIC_CUDA(h, cudaMalloc(&h->stage_out[b], out_need));
+    h->stage_out_bytes = out_need;
+  }
+  int64_t idx = 0;
+  for (int64_t u0 = 0; u0 < units; u0 += upc, ++idx) {
+    const int b = (int)(idx & 1);
+    int64_t nu = std::min<int64_t>(upc, units - u0);
+    // staging buffer b is free once the D2H (or compute) of chunk idx-2 finished
+    if (idx >= 2) {
+      TIC_CUDA(h, cudaStreamWaitEvent(h->s_h2d, inout_same ? h->ev_out[b] : h->ev_comp[b], 0));
+    }
+    TIC_CUDA(h, cudaMemcpyAsync(h->stage_in[b], (const char*)in + (size_t)u0 * in_unit_bytes, (size_t)nu * in_unit_bytes,
+                                cudaMemcpyHostToDevice, h->s_h2d));
+    TIC_CUDA(h, cudaEventRecord(h->ev_in[b], h->s_h2d));
+    TIC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+    if (idx >= 2 && !inout_same) TIC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));
+    void* dout = inout_same ? h->stage_in[b] : h->stage_out[b];
+    int rc = run(h->stage_in[b], dout, 0, nu, /*local=*/true);
+    if (rc != TIC_OK) return rc;
+    TIC_CUDA(h, cudaEventRecord(h->ev_comp[b], h->stream));
+    TIC_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+    TIC_CUDA(h, cudaMemcpyAsync((char*)out + (size_t)u0 * out_unit_bytes, dout, (size_t)nu * out_unit_bytes,
+                                cudaMemcpyDeviceToHost, h->s_d2h));
+    TIC_CUDA(h, cudaEventRecord(h->ev_out[b], h->s_d2h));
+  }
+  TIC_CUDA(h, cudaEventRecord(h->ev_t1, h->stream));
+  TIC_CUDA(h, cudaStreamSynchronize(h->s_d2h));
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TIC_OK;
+}
+
+Geo patch_geo(int P, long long n0) {
+  Geo g{};
+  g.H = P;
+  g.W = P;
+  g.gh = 1;
+  g.gw = 1;
+  g.oy = 0;
+  g.ox = 0;
+  g.P = P;
+  g.n0 = n0;
+  return g;
+}
+
+Geo image_geo(int H, int W, int P, long long n0) {
+  Geo g{};
+  g.H = H;
+  g.W = W;
+  g.gh = (H + P - 1) / P;
+  g.gw = (W + P - 1) / P;
+  g.oy = 0;
+  g.ox = 0;
+  g.P = P;
+  g.n0 = n0;
+  return g;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* tic_version(void) { return "tic-b200 0.1 (sm_100a)"; }
+const char* tic_create_error(void) { return g_create_error.c_str(); }
+
+int tic_create(tic_codec** out, int device) {
+  if (!out) return TIC_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                     " (this library has no CPU fallback)";
+    return TIC_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    g_create_error = "device index out of range";
+    return TIC_ERR_INVALID;
+  }
+  tic_codec* h = new tic_codec();
+  h->device = device;
+  auto bail = [&](const char* what, cudaError_t err) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+    delete h;
+    return TIC_ERR_CUDA;
+  };
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+  h->num_sms = prop.multiProcessorCount;
+  if (prop.major != 10) {
+    g_create_error = "this build targets sm_100a (B200); device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+    delete h;
+    return TIC_ERR_UNSUPPORTED;
+  }
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  h->own_stream = true;
+  if ((e = cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  if ((e = cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking)) != cudaSuccess) return bail("stream", e);
+  for (int b = 0; b < 2; ++b) {
+    cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming);
+  }
+  cudaEventCreate(&h->ev_t0);
+  cudaEventCreate(&h->ev_t1);
+  if ((e = cudaMalloc(&h->d_hist, 256 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
+  cudaMemset(h->d_hist, 0, 256 * sizeof(unsigned long long));
+  if ((e = cudaMalloc(&h->d_symlut, 256 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
+  cudaMemset(h->d_symlut, 0, 256 * sizeof(float));
+  *out = h;
+  return TIC_OK;
+}
+
+void tic_destroy(tic_codec* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int gi = 0; gi < 3; ++gi) {
+    for (auto& l : h->g[gi].layers) {
+      if (l.w) cudaFree(l.w);
+      if (l.b) cudaFree(l.b);
+      l.uw.release();
+    }
+    if (h->g[gi].d_normlut) cudaFree(h->g[gi].d_normlut);
+  }
+  for (int i = 0; i < 3; ++i)
+    if (h->act[i]) cudaFree(h->act[i]);
+  for (int b = 0; b < 2; ++b) {
+    if (h->stage_in[b]) cudaFree(h->stage_in[b]);
+    if (h->stage_out[b]) cudaFree(h->stage_out[b]);
+    cudaEventDestroy(h->ev_in[b]);
+    cudaEventDestroy(h->ev_comp[b]);
+    cudaEventDestroy(h->ev_out[b]);
+  }
+  cudaEventDestroy(h->ev_t0);
+  cudaEventDestroy(h->ev_t1);
+  if (h->d_hist) cudaFree(h->d_hist);
+  if (h->d_symlut) cudaFree(h->d_symlut);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  delete h;
+}
+
+const char* tic_last_error(const tic_codec* h) { return h ? h->err.c_str() : "null handle"; }
+
+int tic_set_stream(tic_codec* h, void* cuda_stream) {
+  if (!h) return TIC_ERR_INVALID;
+  if (h->own_stream && h->stream) {
+    cudaStreamSynchronize(h->stream);
+    cudaStreamDestroy(h->stream);
+  }
+  h->stream = (cudaStream_t)cuda_stream;
+  h->own_stream = false;
+  return TIC_OK;
+}
+
+int tic_set_compute_mode(tic_codec* h, int mode) {
+  if (!h) return TIC_ERR_INVALID;
+  if (mode < TIC_COMPUTE_FP32 || mode > TIC_COMPUTE_TENSOR_TF32) return fail(h, TIC_ERR_INVALID, "unknown compute mode %d", mode);
+  h->mode = mode;
+  return TIC_OK;
+}
+
+int tic_set_chunk_patches(tic_codec* h, int chunk) {
+  if (!h || chunk <= 0) return h ? fail(h, TIC_ERR_INVALID, "chunk must be positive") : TIC_ERR_INVALID;
+  h->chunk128 = chunk;
+  return TIC_OK;
+}
+
+int tic_set_graph(tic_codec* h, int graph, const tic_layer_desc* layers, int n_layers) {
+  if (!h) return TIC_ERR_INVALID;
+  if (graph < 0 || graph > 2 || !layers || n_layers <= 0) return fail(h, TIC_ERR_INVALID, "bad graph arguments");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  int prev = -1;
+  bool open_res = false;
+  for (int i = 0; i < n_layers; ++i) {
+    const tic_layer_desc& d = layers[i];
+    if (d.kind != TIC_CONV && d.kind != TIC_DECONV) return fail(h, TIC_ERR_INVALID, "layer %d: bad kind", i);
+    if (d.cin <= 0 || d.cout <= 0 || d.cin > 1024 || d.cout > 1024) return fail(h, TIC_ERR_INVALID, "layer %d: bad channels", i);
+    if (d.kind == TIC_CONV && d.stride != 1 && d.stride != 2) return fail(h, TIC_ERR_INVALID, "layer %d: conv stride must be 1 or 2", i);
+    if (d.kind == TIC_DECONV && d.stride != 2) return fail(h, TIC_ERR_INVALID, "layer %d: deconv stride must be 2", i);
+    if (prev >= 0 && d.cin != prev) return fail(h, TIC_ERR_INVALID, "layer %d: cin %d != previous cout %d", i, d.cin, prev);
+    if (d.res_begin) {
+      if (open_res || i == 0) return fail(h, TIC_ERR_INVALID, "layer %d: bad res_begin", i);
+      open_res = true;
+    }
+    if (d.res_end) {
+      if (!open_res || d.kind != TIC_CONV || d.stride != 1) return fail(h, TIC_ERR_INVALID, "layer %d: bad res_end", i);
+      open_res = false;
+    }
+    if (open_res && (d.kind != TIC_CONV || d.stride != 1 || d.cin != d.cout))
+      return fail(h, TIC_ERR_INVALID, "layer %d: residual blocks need stride-1 convs with cin == cout", i);
+    if (i == n_layers - 1 && open_res) return fail(h, TIC_ERR_INVALID, "unterminated residual block");
+    prev = d.cout;
+  }
+  Graph& g = h->g[graph];
+  for (auto& l : g.layers) {
+    if (l.w) cudaFree(l.w);
+    if (l.b) cudaFree(l.b);
+    l.uw.release();
+  }
+  g.layers.assign(n_layers, Layer());
+  for (int i = 0; i < n_layers; ++i) {
+    Layer& l = g.layers[i];
+    l.d = layers[i];
+    TIC_CUDA(h, cudaMalloc(&l.w, (size_t)9 * l.d.cin * l.d.cout * sizeof(float)));
+    TIC_CUDA(h, cudaMalloc(&l.b, (size_t)l.d.cout * sizeof(float)));
+  }
+  return TIC_OK;
+}
+
+int tic_load_weights(tic_codec* h, int graph, int layer, const float* kernel, const float* bias) {
+  if (!h) return TIC_ERR_INVALID;
+  if (graph < 0 || graph > 2 || !kernel || !bias) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  Graph& g = h->g[graph];
+  if (layer < 0 || layer >= (int)g.layers.size()) return fail(h, TIC_ERR_INVALID, "layer index %d out of range", layer);
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  Layer& l = g.layers[layer];
+  const int cin = l.d.cin, cout = l.d.cout;
+  std::vector<float> w((size_t)9 * cin * cout);
+  if (l.d.kind == TIC_CONV) {
+    // TF HWIO [3][3][cin][cout] is already [tap][cin][cout]
+    std::memcpy(w.data(), kernel, w.size() * sizeof(float));
+  } else {
+    // TF conv2d_transpose filter [3][3][cout][cin] (basic_block.py:53) -> [tap][cin][cout]
+    for (int t = 0; t < 9; ++t)
+      for (int oc = 0; oc < cout; ++oc)
+        for (int ic = 0; ic < cin; ++ic) w[((size_t)t * cin + ic) * cout + oc] = kernel[((size_t)t * cout + oc) * cin + ic];
+  }
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  TIC_CUDA(h, cudaMemcpy(l.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  TIC_CUDA(h, cudaMemcpy(l.b, bias, (size_t)cout * sizeof(float), cudaMemcpyHostToDevice));
+  l.uw.release();
+  l.loaded = true;
+  return TIC_OK;
+}
+
+int tic_set_norm(tic_codec* h, int graph, const float* mean3, const float* std3) {
+  if (!h) return TIC_ERR_INVALID;
+  if (graph < 0 || graph > 2 || !mean3 || !std3) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  Graph& g = h->g[graph];
+  std::vector<float> lut(3 * 256);
+  for (int c = 0; c < 3; ++c) {
+    if (!(std3[c] != 0.0f)) return fail(h, TIC_ERR_INVALID, "std[%d] is zero", c);
+    g.mean[c] = mean3[c];
+    g.stdv[c] = std3[c];
+    for (int v = 0; v < 256; ++v) lut[c * 256 + v] = tic_normalize((float)v, mean3[c], std3[c]);
+  }
+  if (!g.d_normlut) TIC_CUDA(h, cudaMalloc(&g.d_normlut, lut.size() * sizeof(float)));
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  TIC_CUDA(h, cudaMemcpy(g.d_normlut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice));
+  g.has_norm = true;
+  return TIC_OK;
+}
+
+int tic_set_quantizer(tic_codec* h, int quan_scale, const float* inv_sigmoid_lut) {
+  if (!h) return TIC_ERR_INVALID;
+  if (quan_scale < 2 || quan_scale > 256 || !inv_sigmoid_lut)
+    return fail(h, TIC_ERR_INVALID, "quan_scale must be in [2, 256] (symbols are stored as uint8)");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  TIC_CUDA(h, cudaMemcpy(h->d_symlut, inv_sigmoid_lut, (size_t)quan_scale * sizeof(float), cudaMemcpyHostToDevice));
+  h->q = quan_scale;
+  return TIC_OK;
+}
+
+int tic_bottleneck_shape(tic_codec* h, int P, int* hb, int* wb, int* cb) {
+  if (!h) return TIC_ERR_INVALID;
+  Graph& g = h->g[TIC_GRAPH_ENCODER];
+  if (g.layers.empty()) return fail(h, TIC_ERR_STATE, "encoder graph not configured");
+  Shape so;
+  if (graph_out_shape(g, Shape{P, P, g.layers[0].d.cin}, &so, nullptr) != 0) return fail(h, TIC_ERR_INVALID, "inconsistent graph");
+  if (hb) *hb = so.h;
+  if (wb) *wb = so.w;
+  if (cb) *cb = so.c;
+  return TIC_OK;
+}
+
+// ---- hot path ---------------------------------------------------------------------------------
+int tic_encode_patches(tic_codec* h, const void* patches, int in_dtype, int64_t n, int P, void* symbols,
+                       int out_dtype, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n < 0 || P <= 0 || (n > 0 && (!patches || !symbols))) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  if (in_dtype != TIC_U8 && in_dtype != TIC_F32) return fail(h, TIC_ERR_INVALID, "bad in_dtype");
+  if (out_dtype != TIC_U8 && out_dtype != TIC_F32) return fail(h, TIC_ERR_INVALID, "bad out_dtype");
+  int rc = check_graph_ready(h, TIC_GRAPH_ENCODER, true);
+  if (rc != TIC_OK) return rc;
+  if (h->q < 2) return fail(h, TIC_ERR_STATE, "quantiser not configured (tic_set_quantizer)");
+  if (h->g[TIC_GRAPH_ENCODER].layers[0].d.cin != 3) return fail(h, TIC_ERR_INVALID, "encoder must take 3 channels");
+  int hb, wb, cb;
+  rc = tic_bottleneck_shape(h, P, &hb, &wb, &cb);
+  if (rc != TIC_OK) return rc;
+  const size_t in_unit = (size_t)P * P * 3 * (in_dtype == TIC_U8 ? 1 : 4);
+  const size_t out_unit = (size_t)hb * wb * cb * (out_dtype == TIC_U8 ? 1 : 4);
+  return drive(h, mem, patches, symbols, n, patches_per_chunk(h, P), in_unit, out_unit, false,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 IoSpec i, o;
+                 i.mode = in_dtype == TIC_U8 ? IO_U8_NORM : IO_F32_NORM;
+                 i.in = din;
+                 i.geo = patch_geo(P, u0);
+                 o.mode = out_dtype == TIC_U8 ? IO_QUANT_U8 : IO_QUANT_F32;
+                 o.out = dout;
+                 o.geo = patch_geo(P, u0);
+                 return run_graph(h, TIC_GRAPH_ENCODER, i, o, (int)nu, P, P);
+               });
+}
+
+int tic_encode_images(tic_codec* h, const uint8_t* images, int64_t n_images, int H, int W, int P, uint8_t* symbols,
+                      int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n_images < 0 || H <= 0 || W <= 0 || P <= 0 || (n_images > 0 && (!images || !symbols)))
+    return fail(h, TIC_ERR_INVALID, "bad arguments");
+  if ((H % P != 0 && H < 2) || (W % P != 0 && W < 2)) return fail(h, TIC_ERR_INVALID, "reflect padding needs at least 2 pixels");
+  int rc = check_graph_ready(h, TIC_GRAPH_ENCODER, true);
+  if (rc != TIC_OK) return rc;
+  if (h->q < 2) return fail(h, TIC_ERR_STATE, "quantiser not configured (tic_set_quantizer)");
+  if (h->g[TIC_GRAPH_ENCODER].layers[0].d.cin != 3) return fail(h, TIC_ERR_INVALID, "encoder must take 3 channels");
+  int hb, wb, cb;
+  rc = tic_bottleneck_shape(h, P, &hb, &wb, &cb);
+  if (rc != TIC_OK) return rc;
+  const Geo g0 = image_geo(H, W, P, 0);
+  const int ppi = g0.gh * g0.gw;
+  const int64_t ipc = std::max<int64_t>(1, patches_per_chunk(h, P) / ppi);
+  const size_t in_unit = (size_t)H * W * 3;
+  const size_t out_unit = (size_t)ppi * hb * wb * cb;
+  return drive(h, mem, images, symbols, n_images, ipc, in_unit, out_unit, false,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 IoSpec i, o;
+                 i.mode = IO_U8_NORM;
+                 i.in = din;
+                 i.geo = image_geo(H, W, P, u0 * ppi);
+                 o.mode = IO_QUANT_U8;
+                 o.out = dout;
+                 o.geo = i.geo;
+                 return run_graph(h, TIC_GRAPH_ENCODER, i, o, (int)(nu * ppi), P, P);
+               });
+}
+
+int tic_decode_patches(tic_codec* h, const uint8_t* symbols, int64_t n, int hb, int wb, float* recon, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n < 0 || hb <= 0 || wb <= 0 || (n > 0 && (!symbols || !recon))) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  int rc = check_graph_ready(h, TIC_GRAPH_DECODER, true);
+  if (rc != TIC_OK) return rc;
+  if (h->q < 2) return fail(h, TIC_ERR_STATE, "quantiser not configured (tic_set_quantizer)");
+  Graph& g = h->g[TIC_GRAPH_DECODER];
+  const int cb = g.layers[0].d.cin;
+  Shape so;
+  if (graph_out_shape(g, Shape{hb, wb, cb}, &so, nullptr) != 0) return fail(h, TIC_ERR_INVALID, "inconsistent graph");
+  if (so.c != 3 || so.h != so.w) return fail(h, TIC_ERR_INVALID, "decoder must produce square RGB patches (got %dx%dx%d)", so.h, so.w, so.c);
+  const int P = so.h;
+  return drive(h, mem, symbols, recon, n, patches_per_chunk(h, P), (size_t)hb * wb * cb, (size_t)P * P * 3 * 4, false,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 IoSpec i, o;
+                 i.mode = IO_U8_SYMLUT;
+                 i.in = din;
+                 i.geo = patch_geo(P, u0);
+                 o.mode = IO_DENORM_F32;
+                 o.out = dout;
+                 o.geo = patch_geo(P, u0);
+                 return run_graph(h, TIC_GRAPH_DECODER, i, o, (int)nu, hb, wb);
+               });
+}
+
+int tic_decode_images(tic_codec* h, const uint8_t* symbols, int64_t n_images, int H, int W, int P, void* images,
+                      int out_dtype, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n_images < 0 || H <= 0 || W <= 0 || P <= 0 || (n_images > 0 && (!symbols || !images)))
+    return fail(h, TIC_ERR_INVALID, "bad arguments");
+  if (out_dtype != TIC_U8 && out_dtype != TIC_F32) return fail(h, TIC_ERR_INVALID, "bad out_dtype");
+  int rc = check_graph_ready(h, TIC_GRAPH_DECODER, true);
+  if (rc != TIC_OK) return rc;
+  if (h->q < 2) return fail(h, TIC_ERR_STATE, "quantiser not configured (tic_set_quantizer)");
+  Graph& g = h->g[TIC_GRAPH_DECODER];
+  const int cb = g.layers[0].d.cin;
+  // bottleneck map size for patch size P: invert the decoder's upsampling
+  int up = 1;
+  for (auto& l : g.layers)
+    if (l.d.kind == TIC_DECONV) up *= 2;
+  if (P % up != 0) return fail(h, TIC_ERR_INVALID, "patch size %d is not a multiple of the decoder upsampling %d", P, up);
+  const int hb = P / up, wb = P / up;
+  Shape so;
+  if (graph_out_shape(g, Shape{hb, wb, cb}, &so, nullptr) != 0 || so.c != 3 || so.h != P)
+    return fail(h, TIC_ERR_INVALID, "decoder graph does not map %dx%d symbols to %dx%d RGB", hb, wb, P, P);
+  const Geo g0 = image_geo(H, W, P, 0);
+  const int ppi = g0.gh * g0.gw;
+  const int64_t ipc = std::max<int64_t>(1, patches_per_chunk(h, P) / ppi);
+  const size_t in_unit = (size_t)ppi * hb * wb * cb;
+  const size_t out_unit = (size_t)H * W * 3 * (out_dtype == TIC_U8 ? 1 : 4);
+  return drive(h, mem, symbols, images, n_images, ipc, in_unit, out_unit, false,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 IoSpec i, o;
+                 i.mode = IO_U8_SYMLUT;
+                 i.in = din;
+                 i.geo = image_geo(H, W, P, u0 * ppi);
+                 o.mode = out_dtype == TIC_U8 ? IO_DENORM_U8 : IO_DENORM_F32;
+                 o.out = dout;
+                 o.geo = i.geo;
+                 return run_graph(h, TIC_GRAPH_DECODER, i, o, (int)(nu * ppi), hb, wb);
+               });
+}
+
+int tic_postfilter_patches(tic_codec* h, const float* tiles, int64_t n, int P, float* out, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n < 0 || P <= 0 || (n > 0 && (!tiles || !out))) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  int rc = check_graph_ready(h, TIC_GRAPH_POSTFILTER, true);
+  if (rc != TIC_OK) return rc;
+  Graph& g = h->g[TIC_GRAPH_POSTFILTER];
+  Shape so;
+  if (g.layers[0].d.cin != 3 || graph_out_shape(g, Shape{P, P, 3}, &so, nullptr) != 0 || so.c != 3 || so.h != P || so.w != P)
+    return fail(h, TIC_ERR_INVALID, "post-filter graph must map PxPx3 to PxPx3");
+  const size_t unit = (size_t)P * P * 3 * 4;
+  return drive(h, mem, tiles, out, n, patches_per_chunk(h, P), unit, unit, false,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 IoSpec i, o;
+                 i.mode = IO_F32_NORM;
+                 i.in = din;
+                 i.geo = patch_geo(P, u0);
+                 o.mode = IO_DENORM_F32;
+                 o.out = dout;
+                 o.geo = patch_geo(P, u0);
+                 return run_graph(h, TIC_GRAPH_POSTFILTER, i, o, (int)nu, P, P);
+               });
+}
+
+int tic_postfilter_images(tic_codec* h, float* images, int64_t n_images, int H, int W, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n_images < 0 || H <= 0 || W <= 0 || (n_images > 0 && !images)) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  int rc = check_graph_ready(h, TIC_GRAPH_POSTFILTER, true);
+  if (rc != TIC_OK) return rc;
+  Graph& g = h->g[TIC_GRAPH_POSTFILTER];
+  const int P = 128, off = 64;  // submit/2/rmbe/rmbe.py:12,16
+  Shape so;
+  if (g.layers[0].d.cin != 3 || graph_out_shape(g, Shape{P, P, 3}, &so, nullptr) != 0 || so.c != 3 || so.h != P || so.w != P)
+    return fail(h, TIC_ERR_INVALID, "post-filter graph must map 128x128x3 to 128x128x3");
+  const size_t unit = (size_t)H * W * 3 * 4;
+  // tiles per image of the two passes; whole images per chunk so that pass 2 reads pass-1 output
+  const int t1 = (H / P) * ((W - off) / P), t2 = ((H - off) / P) * (W / P);
+  const int64_t ipc = std::max<int64_t>(1, patches_per_chunk(h, P) / std::max(1, std::max(t1, t2)));
+  return drive(h, mem, images, images, n_images, ipc, unit, unit, true,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 (void)din;
+                 for (int pass = 0; pass < 2; ++pass) {
+                   Geo gg{};
+                   gg.H = H;
+                   gg.W = W;
+                   gg.P = P;
+                   if (pass == 0) {  // rmbe_height: rows i*128, cols 64 + j*128 (rmbe.py:70-89)
+                     gg.gh = H / P;
+                     gg.gw = W >= off ? (W - off) / P : 0;
+                     gg.oy = 0;
+                     gg.ox = off;
+                   } else {          // rmbe_width: rows 64 + i*128, cols j*128 (rmbe.py:92-111)
+                     gg.gh = H >= off ? (H - off) / P : 0;
+                     gg.gw = W / P;
+                     gg.oy = off;
+                     gg.ox = 0;
+                   }
+                   const int tiles = gg.gh * gg.gw;
+                   if (tiles <= 0) continue;
+                   gg.n0 = u0 * tiles;
+                   IoSpec i, o;
+                   i.mode = IO_F32_NORM;
+                   i.in = dout;  // in place: pass 2 reads what pass 1 wrote
+                   i.geo = gg;
+                   o.mode = IO_DENORM_F32;
+                   o.out = dout;
+                   o.geo = gg;
+                   int r2 = run_graph(h, TIC_GRAPH_POSTFILTER, i, o, (int)(nu * tiles), P, P);
+                   if (r2 != TIC_OK) return r2;
+                 }
+                 return (int)TIC_OK;
+               });
+}
+
+int tic_run_layers(tic_codec* h, int graph, const float* in, int64_t n, int h0, int w0, int n_layers, float* out,
+                   int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (graph < 0 || graph > 2 || n < 0 || h0 <= 0 || w0 <= 0 || n_layers <= 0 || (n > 0 && (!in || !out)))
+    return fail(h, TIC_ERR_INVALID, "bad arguments");
+  int rc = check_graph_ready(h, graph, false);
+  if (rc != TIC_OK) return rc;
+  Graph& g = h->g[graph];
+  if (n_layers > (int)g.layers.size()) return fail(h, TIC_ERR_INVALID, "graph has only %zu layers", g.layers.size());
+  if (g.layers[n_layers - 1].d.res_begin) return fail(h, TIC_ERR_INVALID, "cannot stop inside a residual block");
+  const int cin = g.layers[0].d.cin;
+  Shape so;
+  if (graph_out_shape(g, Shape{h0, w0, cin}, &so, nullptr, n_layers) != 0) return fail(h, TIC_ERR_INVALID, "inconsistent graph");
+  const size_t in_unit = (size_t)h0 * w0 * cin * 4, out_unit = (size_t)so.h * so.w * so.c * 4;
+  const int64_t upc = std::max<int64_t>(1, (int64_t)h->chunk128 * 128 * 128 / ((int64_t)std::max(h0 * w0, so.h * so.w)));
+  return drive(h, mem, in, out, n, upc, in_unit, out_unit, false,
+               [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+                 IoSpec i, o;
+                 i.mode = IO_ACT;
+                 i.in = (const char*)din + (size_t)u0 * in_unit;
+                 o.mode = IO_ACT;
+                 o.out = (char*)dout + (size_t)u0 * out_unit;
+                 return run_graph(h, graph, i, o, (int)nu, h0, w0, n_layers);
+               });
+}
+
+int tic_round_u8(tic_codec* h, const float* src, uint8_t* dst, int64_t count, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (count < 0 || (count > 0 && (!src || !dst))) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  const int64_t upc = 1 << 26;
+  return drive(h, mem, src, dst, count, upc, 4, 1, false, [&](const void* din, void* dout, int64_t u0, int64_t nu, bool) {
+    const float* s = (const float*)din + u0;
+    uint8_t* d = (uint8_t*)dout + u0;
+    int blocks = (int)std::min<int64_t>((nu + 255) / 256, (int64_t)h->num_sms * 16);
+    round_u8_kernel<<<blocks, 256, 0, h->stream>>>(s, d, nu);
+    h->launches++;
+    TIC_CUDA(h, cudaGetLastError());
+    return (int)TIC_OK;
+  });
+}
+
+// ---- statistics -------------------------------------------------------------------------------
+int tic_hist_reset(tic_codec* h) {
+  if (!h) return TIC_ERR_INVALID;
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  TIC_CUDA(h, cudaMemsetAsync(h->d_hist, 0, 256 * sizeof(unsigned long long), h->stream));
+  return TIC_OK;
+}
+
+int tic_hist_read(tic_codec* h, uint64_t* counts, int q) {
+  if (!h) return TIC_ERR_INVALID;
+  if (!counts || q <= 0 || q > 256) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  TIC_CUDA(h, cudaMemcpyAsync(counts, h->d_hist, (size_t)q * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TIC_OK;
+}
+
+int tic_hist_device_ptr(tic_codec* h, void** dev_ptr) {
+  if (!h || !dev_ptr) return TIC_ERR_INVALID;
+  *dev_ptr = h->d_hist;
+  return TIC_OK;
+}
+
+int tic_position_sums(tic_codec* h, const uint8_t* symbols, int64_t n, int64_t npos, uint64_t* sums, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n < 0 || npos <= 0 || !sums || (n > 0 && !symbols)) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  const uint8_t* dsym = symbols;
+  unsigned long long* dsum = (unsigned long long*)sums;
+  void *tmp_sym = nullptr, *tmp_sum = nullptr;
+  if (mem == TIC_MEM_HOST) {
+    TIC_CUDA(h, cudaMalloc(&tmp_sym, (size_t)std::max<int64_t>(1, n * npos)));
+    TIC_CUDA(h, cudaMalloc(&tmp_sum, (size_t)npos * 8));
+    TIC_CUDA(h, cudaMemcpyAsync(tmp_sym, symbols, (size_t)(n * npos), cudaMemcpyHostToDevice, h->stream));
+    TIC_CUDA(h, cudaMemcpyAsync(tmp_sum, sums, (size_t)npos * 8, cudaMemcpyHostToDevice, h->stream));
+    dsym = (const uint8_t*)tmp_sym;
+    dsum = (unsigned long long*)tmp_sum;
+  }
+  position_sums_kernel<<<(unsigned)((npos + 255) / 256), 256, 0, h->stream>>>(dsym, n, npos, dsum);
+  h->launches++;
+  TIC_CUDA(h, cudaGetLastError());
+  if (mem == TIC_MEM_HOST) {
+    TIC_CUDA(h, cudaMemcpyAsync(sums, tmp_sum, (size_t)npos * 8, cudaMemcpyDeviceToHost, h->stream));
+    TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(tmp_sym);
+    cudaFree(tmp_sum);
+  }
+  return TIC_OK;
+}
+
+static int prof_collect(tic_codec* h) {
+  for (auto& r : h->prof_pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.e1);
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    auto& v = h->prof_ms[r.graph];
+    auto& c = h->prof_n[r.graph];
+    if ((int)v.size() <= r.layer) {
+      v.resize(r.layer + 1, 0.f);
+      c.resize(r.layer + 1, 0);
+    }
+    v[r.layer] += ms;
+    c[r.layer] += 1;
+  }
+  h->prof_pending.clear();
+  return TIC_OK;
+}
+
+int tic_profile_enable(tic_codec* h, int on) {
+  if (!h) return TIC_ERR_INVALID;
+  h->profile = on != 0;
+  return TIC_OK;
+}
+
+int tic_profile_reset(tic_codec* h) {
+  if (!h) return TIC_ERR_INVALID;
+  prof_collect(h);
+  for (int g = 0; g < 3; ++g) {
+    h->prof_ms[g].clear();
+    h->prof_n[g].clear();
+  }
+  return TIC_OK;
+}
+
+int tic_profile_read(tic_codec* h, int graph, float* ms, int64_t* launches, int n_layers) {
+  if (!h) return TIC_ERR_INVALID;
+  if (graph < 0 || graph > 2 || !ms || !launches || n_layers <= 0) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  prof_collect(h);
+  for (int i = 0; i < n_layers; ++i) {
+    ms[i] = i < (int)h->prof_ms[graph].size() ? h->prof_ms[graph][i] : 0.f;
+    launches[i] = i < (int)h->prof_n[graph].size() ? h->prof_n[graph][i] : 0;
+  }
+  return TIC_OK;
+}
+
+int64_t tic_launch_count(const tic_codec* h) { return h ? h->launches : 0; }
+
+float tic_last_kernel_ms(const tic_codec* h) {
+  if (!h) return 0.f;
+  float ms = 0.f;
+  if (cudaEventSynchronize(h->ev_t1) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+// Shared device-side types for the codec kernels: fused-I/O geometry (crop / stitch by index
+// arithmetic), per-layer launch arguments, first-layer prologue and last-layer epilogue helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tic_math.h"
+
+namespace tic {
+
+// How the first layer reads its input / the last layer writes its output.
+enum IoMode : int {
+  IO_ACT = 0,          // f32 NHWC activation [n,h,w,c] (workspace)
+  IO_U8_NORM = 1,      // in: u8 pixels through Geo, (x-mean)/std via 3x256 table         (model_0/model.py:44)
+  IO_F32_NORM = 2,     // in: f32 pixels through Geo, (x-mean)/std computed                (model_0/model.py:44)
+  IO_U8_SYMLUT = 3,    // in: u8 symbols [n,h,w,c] through the q-entry inverse-sigmoid LUT (model_0/model.py:153)
+  IO_QUANT_U8 = 4,     // out: sigmoid*(q-1), round -> u8 symbols + histogram              (model_0/model.py:137-138)
+  IO_QUANT_F32 = 5,    // out: same, stored as integer-valued f32 (what sess.run returns)
+  IO_DENORM_F32 = 6,   // out: clip(y*std+mean,0,255) f32 through Geo                      (model_0/model.py:251,259)
+  IO_DENORM_U8 = 7     // out: same then np.around -> u8 through Geo                       (decode.py:249)
+};
+
+// Patch <-> image geometry.  A "patch array" [n,P,P,3] is the degenerate case
+// H = W = P, gh = gw = 1.  utils.crop_image_input_patches (utils/utils.py:96-133) pads
+// bottom/right with np.pad(...,'reflect') and walks the patch grid row-major;
+// utils.concat_patches (utils/utils.py:136-167) stitches row-major and crops to [H,W];
+// rmbe tiles (submit/2/rmbe/rmbe.py:70-111) are the same grid shifted by (oy, ox).
+struct Geo {
+  int H, W;      // image height / width
+  int gh, gw;    // patch grid per image
+  int oy, ox;    // origin of the grid inside the image
+  int P;         // patch edge
+  long long n0;  // global index of the chunk's first patch
+};
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  // numpy 'reflect' (no edge repeat): period 2(n-1)
+  if (i < n) return i;
+  int period = 2 * (n - 1);
+  if (period <= 0) return 0;
+  int m = i % period;
+  return m < n ? m : period - m;
+}
+
+// pixel (y,x) of global patch g -> element offset (in pixels) inside the image batch, or -1
+// when outside the image and reflect == false.
+__device__ __forceinline__ long long geo_pixel(const Geo& g, long long patch, int y, int x, bool reflect) {
+  int per_img = g.gh * g.gw;
+  long long img = patch / per_img;
+  int r = (int)(patch - img * per_img);
+  int gy = r / g.gw, gx = r - gy * g.gw;
+  int Y = g.oy + gy * g.P + y;
+  int X = g.ox + gx * g.P + x;
+  if (reflect) {
+    Y = reflect_index(Y, g.H);
+    X = reflect_index(X, g.W);
+  } else if (Y >= g.H || X >= g.W) {
+    return -1;
+  }
+  return (img * g.H + Y) * (long long)g.W + X;
+}
+
+struct LayerArgs {
+  const void* in;        // first layer: caller input (u8 / f32); else f32 activation
+  void* out;             // last layer: caller output; else f32 activation
+  const float* wgt;      // [9][cin][cout] fp32 (tap-major, cout contiguous)
+  const float* bias;     // [cout]
+  const float* res;      // residual source [n,hout,wout,cout] or nullptr
+  int n;                 // patches in this chunk
+  int hin, win, cin;
+  int hout, wout, cout;
+  int pad_t, pad_l;      // TF SAME padding before (conv)
+  int TW, TH, TP;        // CTA tile: columns, rows, patches (conv: output px; deconv: input px)
+  int tiles_x, tiles_y;
+  int act;
+  int in_mode, out_mode;
+  Geo geo;               // used by the *_NORM / DENORM_* modes
+  const float* lut;      // IO_U8_NORM: [3][256]; IO_U8_SYMLUT: [q]
+  float mean[3], stdv[3];
+  int q;
+  unsigned long long* hist;  // [256] symbol counts (IO_QUANT_*)
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) { return act ? fmaxf(v, 0.0f) : v; }
+
+}  // namespace tic

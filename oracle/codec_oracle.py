@@ -147,6 +147,22 @@ def init_params(layers, cin, seed, scheme="reference"):
     return params
 
 
+def condition_decoder(variant, dec_params, quan_scale, target_std=0.4):
+    """Fixture helper (not reference behaviour): rescale the LAST decoder kernel of a random parameter set
+    so the pre-denormalisation output has std ~target_std.  The decoder input is the inverse-sigmoid table
+    (-13.8 / +11.6 for q = 2), so an unscaled random decoder saturates 0..255 and the 1e-3 max-abs parity
+    bound (0..255 scale) would be compared against pre-clip values of magnitude 1e2..1e4."""
+    v = VARIANTS[variant]
+    hb = 4
+    sym = np.random.RandomState(99).randint(0, quan_scale, size=(2, hb, hb, v["bottleneck"]))
+    x = inverse_sigmoid_lut(quan_scale)[sym]
+    y = run_layers(x, v["dec"], v["bottleneck"], dec_params)
+    last = expand_layers(v["dec"], v["bottleneck"])[-1]["scope"]
+    out = dict(dec_params)
+    out[last + "/kernel"] = (dec_params[last + "/kernel"] * np.float32(target_std / max(float(y.std()), 1e-12))).astype(np.float32)
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # TF op semantics
 # --------------------------------------------------------------------------------------------

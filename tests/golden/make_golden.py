@@ -19,6 +19,7 @@ def main():
     ov = O.VARIANTS["model_0"]
     enc = O.init_params(ov["enc"], 3, 1234, "fanin")
     dec = O.init_params(ov["dec"], ov["bottleneck"], 1235, "fanin")
+    dec = O.condition_decoder("model_0", dec, 2)  # O(1) pre-denormalisation output
     mean, std = O.online_mean_and_std_channel([image])
     mean = np.asarray(mean, np.float32)
     std = np.asarray(std, np.float32)

@@ -254,6 +254,7 @@ def test_golden_fixture_cfg1():
     ov = O.VARIANTS["model_0"]
     enc = O.init_params(ov["enc"], 3, 1234, "fanin")
     dec = O.init_params(ov["dec"], ov["bottleneck"], 1235, "fanin")
+    dec = O.condition_decoder("model_0", dec, 2)
     chk = [float(sum(np.float64(v).sum() for v in enc.values())), float(sum(np.float64(v).sum() for v in dec.values()))]
     np.testing.assert_allclose(chk, z["weight_checksum"], rtol=0, atol=1e-9)
     codec = T.Codec("model_0", quan_scale=2, mean=z["mean"], std=z["std"], enc_params=enc, dec_params=dec)

@@ -46,7 +46,9 @@ def _is_torch(x):
 class _Buf:
     """Pointer + placement of a numpy array or a torch tensor (CPU or CUDA), kept alive while in use."""
 
-    def __init__(self, x, dtype, device_index):
+    def __init__(self, x, dtype, device_index, codec=None):
+        if codec is not None and _is_torch(x) and x.is_cuda:
+            codec._follow_torch_stream()
         self.keep = x
         if _is_torch(x):
             want = {np.uint8: torch.uint8, np.float32: torch.float32}[dtype]
@@ -160,6 +162,14 @@ class Codec:
     def set_chunk_patches(self, chunk):
         self._check(self.lib.tic_set_chunk_patches(self._h, int(chunk)))
 
+    def _follow_torch_stream(self):
+        """Device-tensor calls are asynchronous on torch's CURRENT stream (like any torch op), so later
+        torch work on that stream — .cpu(), comparisons, NCCL — is ordered after the codec's kernels."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if getattr(self, "_stream", None) != s:
+            self._check(self.lib.tic_set_stream(self._h, C.c_void_p(s)))
+            self._stream = s
+
     def use_torch_stream(self, stream=None):
         """Run on a torch CUDA stream (default: torch's current stream) so torch ops and events order
         against the codec's kernels."""
@@ -202,7 +212,7 @@ class Codec:
         if tuple(patches.shape[1:]) != (P, P, 3):
             raise ValueError(f"patches must be [N,P,P,3], got {tuple(patches.shape)}")
         in_dt = np.uint8 if str(patches.dtype).endswith("uint8") else np.float32
-        src = _Buf(patches, in_dt, self.device)
+        src = _Buf(patches, in_dt, self.device, self)
         hb, wb, cb = self.bottleneck_shape(P)
         if out is None:
             out = self._alloc_like(patches, (n, hb, wb, cb), out_dtype)
@@ -220,7 +230,7 @@ class Codec:
         if images.ndim == 3:
             images = images[None]
         B, H, W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
-        src = _Buf(images, np.uint8, self.device)
+        src = _Buf(images, np.uint8, self.device, self)
         P = int(patch_size)
         hb, wb, cb = self.bottleneck_shape(P)
         gh, gw = -(-H // P), -(-W // P)
@@ -237,7 +247,7 @@ class Codec:
         n, hb, wb, cb = (int(v) for v in symbols.shape)
         if cb != self.dec_layers[0].cin:
             raise ValueError(f"decoder expects {self.dec_layers[0].cin} symbol channels, got {cb}")
-        src = _Buf(symbols, np.uint8, self.device)
+        src = _Buf(symbols, np.uint8, self.device, self)
         up = 2 ** sum(1 for l in self.dec_layers if l.kind == "d")
         down = 1
         for l in self.dec_layers:
@@ -256,7 +266,7 @@ class Codec:
         """decoder + concat_patches (+ np.around -> uint8) fused: symbols [B, gh*gw, hb, wb, cb] uint8 ->
         [B,H,W,3] uint8 (rounded) or float32."""
         B = int(symbols.shape[0])
-        src = _Buf(symbols, np.uint8, self.device)
+        src = _Buf(symbols, np.uint8, self.device, self)
         if out is None:
             out = self._alloc_like(symbols, (B, int(height), int(width), 3), out_dtype)
         else:
@@ -276,7 +286,7 @@ class Codec:
         if self.post_layers is None:
             raise TicError("post-filter not configured (set_postfilter)")
         n, P = int(tiles.shape[0]), int(tiles.shape[1])
-        src = _Buf(tiles, np.float32, self.device)
+        src = _Buf(tiles, np.float32, self.device, self)
         if out is None:
             out = self._alloc_like(tiles, tuple(tiles.shape), np.float32)
         dst = _Buf(out, np.float32, self.device)
@@ -289,7 +299,7 @@ class Codec:
             raise TicError("post-filter not configured (set_postfilter)")
         x = images if images.ndim == 4 else images[None]
         B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
-        buf = _Buf(x, np.float32, self.device)
+        buf = _Buf(x, np.float32, self.device, self)
         self._check(self.lib.tic_postfilter_images(self._h, buf.ptr, B, H, W, buf.mem))
         return images
 
@@ -302,14 +312,14 @@ class Codec:
         h, w = h0, w0
         for l in layers[:n_layers]:
             h, w = ((-(-h // l.stride), -(-w // l.stride)) if l.kind == "c" else (2 * h, 2 * w))
-        src = _Buf(x, np.float32, self.device)
+        src = _Buf(x, np.float32, self.device, self)
         out = self._alloc_like(x, (n, h, w, layers[n_layers - 1].cout), np.float32)
         dst = _Buf(out, np.float32, self.device)
         self._check(self.lib.tic_run_layers(self._h, gid, src.ptr, n, h0, w0, int(n_layers), dst.ptr, src.mem))
         return out
 
     def round_u8(self, x, out=None):
-        src = _Buf(x, np.float32, self.device)
+        src = _Buf(x, np.float32, self.device, self)
         if out is None:
             out = self._alloc_like(x, tuple(x.shape), np.uint8)
         dst = _Buf(out, np.uint8, self.device)
@@ -336,7 +346,7 @@ class Codec:
         """sums[hb*wb*cb] += sum over patches (cal_encoded_distribution.py:111-128)."""
         n = int(symbols.shape[0])
         npos = int(np.prod(symbols.shape[1:]))
-        src = _Buf(symbols, np.uint8, self.device)
+        src = _Buf(symbols, np.uint8, self.device, self)
         if sums is None:
             sums = (torch.zeros(npos, dtype=torch.int64, device=symbols.device) if _is_torch(symbols)
                     else np.zeros(npos, dtype=np.uint64))

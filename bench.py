@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--compute", default=os.environ.get("TIC_COMPUTE", "auto"), help="fp32 | tensor | tf32 | auto")
     ap.add_argument("--cpu-images", type=int, default=2, help="images in the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=int(os.environ.get("TIC_CHUNK", "0")), help="patches per launch sequence (0: library default)")
     ap.add_argument("--layers", action="store_true", help="print the per-layer time table to stderr")
     return ap.parse_args()
 
@@ -192,6 +193,8 @@ def run_b200(args):
         compute = os.environ.get("TIC_DEFAULT_COMPUTE", "fp32")
     codec.set_compute(compute)
     codec.use_torch_stream()
+    if args.chunk > 0:
+        codec.set_chunk_patches(args.chunk)
     B = args.images
     gh, gw = IMG_H // P, IMG_W // P
     hb, wb, cb = codec.bottleneck_shape(P)

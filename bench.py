@@ -190,7 +190,7 @@ def run_b200(args):
     codec = T.Codec(VARIANT, quan_scale=2, mean=MEAN, std=STD, device=local, compute="fp32", seed=1234)
     compute = args.compute
     if compute == "auto":
-        compute = os.environ.get("TIC_DEFAULT_COMPUTE", "fp32")
+        compute = os.environ.get("TIC_DEFAULT_COMPUTE", "tensor")  # 3xTF32 tcgen05 path (parity-green)
     codec.set_compute(compute)
     codec.use_torch_stream()
     if args.chunk > 0:

@@ -54,7 +54,7 @@ struct tic_codec {
   float* d_symlut = nullptr;  // [256]
   unsigned long long* d_hist = nullptr;  // [256]
   int mode = TIC_COMPUTE_FP32;
-  int chunk128 = 1024;
+  int chunk128 = 4096;
   // workspaces
   float* act[3] = {nullptr, nullptr, nullptr};
   size_t act_bytes = 0;
@@ -342,9 +342,10 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
       cudaEventRecord(pr.e0, h->stream);
     }
     if (h->mode != TIC_COMPUTE_FP32 && umma_supported(a, d.kind, d.stride)) {
+      int nl = 0;
       rc = launch_umma(h->stream, a, d.kind, d.stride, ly.w, &ly.uw, h->mode == TIC_COMPUTE_TENSOR_3XTF32,
-                       h->num_sms, &h->err);
-      if (rc == TIC_OK) h->launches++;
+                       h->num_sms, &h->err, &nl);
+      h->launches += nl;
     } else {
       rc = launch_simt(h, a, d.kind, d.stride);
     }

@@ -44,19 +44,21 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
 // pixel (y,x) of global patch g -> element offset (in pixels) inside the image batch, or -1
 // when outside the image and reflect == false.
 __device__ __forceinline__ long long geo_pixel(const Geo& g, long long patch, int y, int x, bool reflect) {
-  int per_img = g.gh * g.gw;
-  long long img = patch / per_img;
-  int r = (int)(patch - img * per_img);
-  int gy = r / g.gw, gx = r - gy * g.gw;
-  int Y = g.oy + gy * g.P + y;
-  int X = g.ox + gx * g.P + x;
+  // 32-bit index arithmetic (host guarantees patch < 2^31); only the final offset is 64-bit
+  const unsigned per_img = (unsigned)(g.gh * g.gw);
+  const unsigned pt = (unsigned)patch;
+  const unsigned img = pt / per_img;
+  const unsigned r = pt - img * per_img;
+  const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+  int Y = g.oy + (int)gy * g.P + y;
+  int X = g.ox + (int)gx * g.P + x;
   if (reflect) {
     Y = reflect_index(Y, g.H);
     X = reflect_index(X, g.W);
   } else if (Y >= g.H || X >= g.W) {
     return -1;
   }
-  return (img * g.H + Y) * (long long)g.W + X;
+  return ((long long)img * g.H + Y) * (long long)g.W + X;
 }
 
 struct LayerArgs {

@@ -59,7 +59,38 @@ __device__ __forceinline__ void stage_tiles(const LayerArgs& a, const SmemPlan& 
                                             int pg, int y_in0, int x_in0, int ic0, int oc0) {
   const int tid = threadIdx.x;
   const int npix = a.TP * sp.ih * sp.iw;
-  if (a.in_mode == IO_ACT && (a.cin & 3) == 0) {
+  if ((a.in_mode == IO_U8_NORM || a.in_mode == IO_F32_NORM) && a.cin == 3) {
+    // first layer: one thread per staged pixel — patch/image geometry, reflect indices and the three
+    // channel fetches are done once per pixel (the compute loop only reads the cin = 3 planes)
+    if (ic0 == 0) {
+      for (int u = tid; u < npix; u += kThreads) {
+        const int ix = u % sp.iw;
+        const int r = u / sp.iw;
+        const int iy = r % sp.ih;
+        const int pp = r / sp.ih;
+        const int n = pg * a.TP + pp, Y = y_in0 + iy, X = x_in0 + ix;
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (n < a.n && Y >= 0 && Y < a.hin && X >= 0 && X < a.win) {
+          const long long off = geo_pixel(a.geo, a.geo.n0 + n, Y, X, true) * 3;
+          if (a.in_mode == IO_U8_NORM) {
+            const uint8_t* q = reinterpret_cast<const uint8_t*>(a.in) + off;
+            v0 = __ldg(a.lut + q[0]);
+            v1 = __ldg(a.lut + 256 + q[1]);
+            v2 = __ldg(a.lut + 512 + q[2]);
+          } else {
+            const float* q = reinterpret_cast<const float*>(a.in) + off;
+            v0 = tic_normalize(q[0], a.mean[0], a.stdv[0]);
+            v1 = tic_normalize(q[1], a.mean[1], a.stdv[1]);
+            v2 = tic_normalize(q[2], a.mean[2], a.stdv[2]);
+          }
+        }
+        float* d = s_in + pp * sp.pstr + iy * sp.iwp + ix;
+        d[0] = v0;
+        d[sp.cstr] = v1;
+        d[2 * sp.cstr] = v2;
+      }
+    }
+  } else if (a.in_mode == IO_ACT && (a.cin & 3) == 0) {
     const float* in = reinterpret_cast<const float*>(a.in);
     for (int u = tid; u < npix * (kIcc / 4); u += kThreads) {
       int c4 = u % (kIcc / 4);

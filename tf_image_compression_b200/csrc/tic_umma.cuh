@@ -63,9 +63,10 @@ struct UmmaParams {
   uint32_t wbuf_bytes;
   int three_pass;
   const uint8_t* wimg;     // weight images, groups consecutive
+  int oc0;                 // first output channel of this launch (layers with cout > 64 run in 64-channel slices)
 };
 
-struct UmmaWeights {
+struct UmmaWeightSlice {
   uint8_t* img = nullptr;
   size_t bytes = 0;
   int mode = -1;
@@ -74,6 +75,12 @@ struct UmmaWeights {
     img = nullptr;
     bytes = 0;
     mode = -1;
+  }
+};
+struct UmmaWeights {
+  UmmaWeightSlice slice[4];  // layers with cout > 64 run as 64-channel slices
+  void release() {
+    for (auto& sl : slice) sl.release();
   }
 };
 
@@ -91,8 +98,8 @@ __host__ __device__ inline int group_tap_index(int mode, int kwi, int j) {  // -
 }
 
 // device [9][cin][cout] fp32 -> grouped, swizzled hi/lo operand images
-__global__ void umma_build_weights_kernel(const float* __restrict__ w, int cin, int cout, int npad, int mode, int KB, int gw,
-                                          uint8_t* __restrict__ img) {
+__global__ void umma_build_weights_kernel(const float* __restrict__ w, int cin, int cout, int oc0, int npad, int mode, int KB,
+                                          int gw, uint8_t* __restrict__ img) {
   const int total_taps = KB * 9;
   const long long total = (long long)total_taps * npad * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -110,7 +117,7 @@ __global__ void umma_build_weights_kernel(const float* __restrict__ w, int cin, 
     }
     int tap = group_tap_index(mode, kwi, j);
     int ic = kb * 32 + k;
-    float v = (oc < cout && ic < cin) ? w[((size_t)tap * cin + ic) * cout + oc] : 0.f;
+    float v = (oc0 + oc < cout && ic < cin) ? w[((size_t)tap * cin + ic) * cout + oc0 + oc] : 0.f;
     // round-to-nearest split (unbiased): hi = rn_tf32(v), lo = rn_tf32(v - hi).  The single-pass mode
     // reads the hi image too (rounded weights, truncated activations).
     float hi = ptx::rn_tf32(v);
@@ -398,17 +405,18 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaParams p, c
                 for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], u[i]);
               }
             }
-            if (valid && c < a.cout) {
+            const int oc = p.oc0 + c;
+            if (valid && oc < a.cout) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                const float b = (c + i < a.cout) ? __ldg(a.bias + c + i) : 0.f;
+                const float b = (oc + i < a.cout) ? __ldg(a.bias + oc + i) : 0.f;
                 v[i] = apply_act(__fadd_rn(v[i], b), a.act);
               }
               if (a.res) {
-                const float* rp = a.res + (((long long)n * a.hout + y) * a.wout + x) * a.cout + c;
+                const float* rp = a.res + (((long long)n * a.hout + y) * a.wout + x) * a.cout + oc;
 #pragma unroll
                 for (int i = 0; i < 16; i += 4) {
-                  if (c + i < a.cout) {
+                  if (oc + i < a.cout) {
                     const float4 r = __ldg(reinterpret_cast<const float4*>(rp + i));
                     v[i] = __fadd_rn(r.x, v[i]);
                     v[i + 1] = __fadd_rn(r.y, v[i + 1]);
@@ -417,7 +425,7 @@ umma_conv_kernel(const __grid_constant__ CUtensorMap tmap, const UmmaParams p, c
                   }
                 }
               }
-              store_pixel<16>(a, n, y, x, c, v, s_hist, h_ones, h_valid);
+              store_pixel<16>(a, n, y, x, oc, v, s_hist, h_ones, h_valid);
             }
           }
         }
@@ -472,14 +480,14 @@ inline bool umma_supported(const LayerArgs& a, int kind, int stride) {
   if (a.cin % 32 != 0 || a.cin > 256) return false;
   const int npad = (a.cout + 15) / 16 * 16;
   const int mode = umma_mode_of(kind, stride);
-  if (npad > 128) return false;
-  if (mode == UMMA_DECONV && npad > 128) return false;
+  if (npad > 256) return false;
+  if (a.cout < 16) return false;  // 3-channel output layers are bandwidth-bound: CUDA-core kernel
   const int Ht = mode == UMMA_DECONV ? a.hin : a.hout, Wt = mode == UMMA_DECONV ? a.win : a.wout;
   if (Wt % 8 != 0) return false;
   if (!(Ht == 8 || Ht % 16 == 0)) return false;
   if (mode == UMMA_S2 && (a.hin != 2 * a.hout || a.win != 2 * a.wout)) return false;
   if (a.out_mode == IO_ACT && (a.cout % 4) != 0) return false;
-  if (a.res && (a.cout % 16) != 0) return false;
+  if (a.res && (a.cout % 4) != 0) return false;
   return true;
 }
 
@@ -497,8 +505,8 @@ inline cudaError_t umma_launch_t(cudaStream_t stream, const CUtensorMap& tm, con
   return cudaGetLastError();
 }
 
-inline int launch_umma(cudaStream_t stream, const LayerArgs& a, int kind, int stride, const float* w_dev, UmmaWeights* uw,
-                       bool three_pass, int num_sms, std::string* err) {
+inline int launch_umma_slice(cudaStream_t stream, const LayerArgs& a, int kind, int stride, const float* w_dev,
+                             UmmaWeightSlice* uw, int oc0, int cs, bool three_pass, int num_sms, std::string* err) {
   auto fail = [&](const char* what, int code) {
     if (err) *err = what;
     return code;
@@ -518,7 +526,8 @@ inline int launch_umma(cudaStream_t stream, const LayerArgs& a, int kind, int st
   p.KB = a.cin / 32;
   p.cin = a.cin;
   p.gw = p.mode == UMMA_DECONV ? 2 : 3;
-  p.npad = (a.cout + 15) / 16 * 16;
+  p.npad = (cs + 15) / 16 * 16;
+  p.oc0 = oc0;
   p.phases = p.mode == UMMA_DECONV ? 4 : 1;
   // accumulator split (accuracy) vs tiles per weight-group load (L2 traffic): keep at least 2 tiles
   if (p.mode == UMMA_DECONV) {
@@ -577,7 +586,7 @@ inline int launch_umma(cudaStream_t stream, const LayerArgs& a, int kind, int st
     if (cudaMalloc(&uw->img, wbytes) != cudaSuccess) return fail("cudaMalloc for weight images failed", -4);
     uw->bytes = wbytes;
     uw->mode = p.mode;
-    umma_build_weights_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, p.npad, p.mode, p.KB, p.gw, uw->img);
+    umma_build_weights_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, p.npad, p.mode, p.KB, p.gw, uw->img);
     if (cudaGetLastError() != cudaSuccess) return fail("weight image kernel failed", -2);
   }
   p.wimg = uw->img;
@@ -617,6 +626,20 @@ inline int launch_umma(cudaStream_t stream, const LayerArgs& a, int kind, int st
   if (e != cudaSuccess) {
     if (err) *err = std::string("tensor-path launch failed: ") + cudaGetErrorString(e);
     return -2;
+  }
+  return 0;
+}
+
+// A layer with more than 64 output channels runs as 64-channel slices (same A tiles, disjoint weight
+// rows and output channels): N = 64 keeps four split accumulators x two tiles inside the 512 TMEM columns.
+inline int launch_umma(cudaStream_t stream, const LayerArgs& a, int kind, int stride, const float* w_dev, UmmaWeights* uw,
+                       bool three_pass, int num_sms, std::string* err, int* launches) {
+  int si = 0;
+  for (int oc0 = 0; oc0 < a.cout; oc0 += 64, ++si) {
+    const int cs = std::min(64, a.cout - oc0);
+    int rc = launch_umma_slice(stream, a, kind, stride, w_dev, &uw->slice[si], oc0, cs, three_pass, num_sms, err);
+    if (rc != 0) return rc;
+    if (launches) ++*launches;
   }
   return 0;
 }

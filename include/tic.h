@@ -59,7 +59,9 @@ typedef enum tic_dtype { TIC_U8 = 0, TIC_F32 = 1 } tic_dtype;
 typedef enum tic_compute_mode {
   TIC_COMPUTE_FP32 = 0,       /* fp32 FMA on CUDA cores: the exact path */
   TIC_COMPUTE_TENSOR_3XTF32 = 1, /* tcgen05 implicit GEMM, error-compensated 3xTF32 split, fp32 accumulate in TMEM */
-  TIC_COMPUTE_TENSOR_TF32 = 2    /* tcgen05 implicit GEMM, single-pass TF32 (fast; symbol mismatch ~1e-4, documented) */
+  TIC_COMPUTE_TENSOR_TF32 = 2,   /* tcgen05 implicit GEMM, single-pass TF32 (fast; symbol mismatch ~1e-4, documented) */
+  TIC_COMPUTE_TENSOR_F16X3 = 3   /* tcgen05 implicit GEMM on fp16 (hi, lo) pairs, three products, activations kept as two fp16
+                                    planes; fp32-class accuracy, |activation| must stay below 65504 */
 } tic_compute_mode;
 
 /* One 3x3 layer.  A res_block (basic_block/basic_block.py:74-93) is two conv layers:

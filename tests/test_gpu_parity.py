@@ -14,7 +14,7 @@ from gpu_common import MEAN, STD, make_codec, params_for, patches_from_images, r
 
 pytestmark = pytest.mark.gpu
 
-MODES = os.environ.get("TIC_TEST_MODES", "fp32").split(",")
+MODES = os.environ.get("TIC_TEST_MODES", "fp32,tensor").split(",")
 
 # (variant, patch size, patches) — every BASELINE.json config plus the free table-driven variants
 LAYER_CASES = [("model_0", 128, 3), ("model_1", 256, 1), ("base_model/input_256", 256, 1), ("base_model/ch_128", 128, 2),

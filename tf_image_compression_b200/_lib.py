@@ -17,7 +17,7 @@ CONV, DECONV = 0, 1
 ACT_IDENTITY, ACT_RELU = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 U8, F32 = 0, 1
-COMPUTE_FP32, COMPUTE_TENSOR_3XTF32, COMPUTE_TENSOR_TF32 = 0, 1, 2
+COMPUTE_FP32, COMPUTE_TENSOR_3XTF32, COMPUTE_TENSOR_TF32, COMPUTE_TENSOR_F16X3 = 0, 1, 2, 3
 
 
 class LayerDesc(C.Structure):

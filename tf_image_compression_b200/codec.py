@@ -154,8 +154,8 @@ class Codec:
         self._check(self.lib.tic_set_norm(self._h, L.GRAPH_POSTFILTER, m.ctypes.data, s.ctypes.data))
 
     def set_compute(self, mode):
-        m = {"fp32": L.COMPUTE_FP32, "tensor": L.COMPUTE_TENSOR_3XTF32, "3xtf32": L.COMPUTE_TENSOR_3XTF32,
-             "tf32": L.COMPUTE_TENSOR_TF32}[mode] if isinstance(mode, str) else int(mode)
+        m = {"fp32": L.COMPUTE_FP32, "tensor": L.COMPUTE_TENSOR_F16X3, "f16x3": L.COMPUTE_TENSOR_F16X3,
+             "3xtf32": L.COMPUTE_TENSOR_3XTF32, "tf32": L.COMPUTE_TENSOR_TF32}[mode] if isinstance(mode, str) else int(mode)
         self._check(self.lib.tic_set_compute_mode(self._h, m))
         self.compute = mode
 

@@ -12,6 +12,7 @@
 #include "../../include/tic.h"
 #include "tic_simt.cuh"
 #include "tic_umma.cuh"
+#include "tic_umma16.cuh"
 
 using namespace tic;
 
@@ -24,6 +25,7 @@ struct Layer {
   float* w = nullptr;     // device [9][cin][cout]
   float* b = nullptr;     // device [cout]
   UmmaWeights uw;         // tensor-path operand images (built lazily from w)
+  U16Weights uw16;        // fp16-pair operand images
   bool loaded = false;
 };
 
@@ -258,6 +260,30 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
   size_t mx = 0;
   Shape so;
   if (graph_out_shape(g, s, &so, &mx, limit) != 0) return fail(h, TIC_ERR_INVALID, "layer channel chain is inconsistent");
+  const bool pair16 = h->mode == TIC_COMPUTE_TENSOR_F16X3;  // intermediate activations are fp16 pair planes
+  // pair mode: f32 / symbol inputs of a tensor-capable first layer are split into a workspace buffer first
+  bool split_input = false;
+  if (pair16 && (io_in.mode == IO_ACT || io_in.mode == IO_U8_SYMLUT)) {
+    LayerArgs t{};
+    const tic_layer_desc& d0 = g.layers[0].d;
+    t.n = n;
+    t.hin = s.h;
+    t.win = s.w;
+    t.cin = s.c;
+    int pb;
+    if (d0.kind == TIC_CONV) {
+      same_pad(s.h, d0.stride, &t.hout, &pb);
+      same_pad(s.w, d0.stride, &t.wout, &pb);
+    } else {
+      t.hout = 2 * s.h;
+      t.wout = 2 * s.w;
+    }
+    t.cout = d0.cout;
+    t.in_mode = IO_ACT16;
+    t.out_mode = L == 1 ? io_out.mode : IO_ACT16;
+    split_input = u16_supported(t, d0.kind, d0.stride);
+  }
+  if (split_input) mx = std::max(mx, (size_t)s.h * s.w * s.c);
   const size_t need = mx * (size_t)n * sizeof(float);
   if (need > h->act_bytes) {
     TIC_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -274,6 +300,19 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
   }
   int cur = -1;            // buffer index holding the current activation (-1: caller input)
   int res_buf = -1;        // buffer holding the residual source
+  if (split_input) {
+    const long long count = (long long)n * s.h * s.w * s.c;
+    __half* hi = reinterpret_cast<__half*>(h->act[0]);
+    const int blocks = (int)std::min<long long>((count + 255) / 256, (long long)h->num_sms * 8);
+    if (io_in.mode == IO_ACT)
+      u16_split_f32_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const float*>(io_in.in), hi, hi + count, count);
+    else
+      u16_split_symlut_kernel<<<blocks, 256, 0, h->stream>>>(
+          reinterpret_cast<const uint8_t*>(io_in.in) + (long long)io_in.geo.n0 * s.h * s.w * s.c, h->d_symlut, hi, hi + count, count);
+    h->launches++;
+    TIC_CUDA(h, cudaGetLastError());
+    cur = 0;
+  }
   for (int i = 0; i < L; ++i) {
     Layer& ly = g.layers[i];
     const tic_layer_desc& d = ly.d;
@@ -300,14 +339,15 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
       a.stdv[c] = g.stdv[c];
     }
     // input
-    if (i == 0) {
+    if (i == 0 && !split_input) {
       a.in = io_in.in;
       a.in_mode = io_in.mode;
       a.geo = io_in.geo;
       a.lut = (io_in.mode == IO_U8_NORM) ? g.d_normlut : (io_in.mode == IO_U8_SYMLUT ? h->d_symlut : nullptr);
     } else {
       a.in = h->act[cur];
-      a.in_mode = IO_ACT;
+      a.in_mode = pair16 ? IO_ACT16 : IO_ACT;
+      a.in_lo_off = (long long)n * a.hin * a.win * a.cin;
     }
     if (d.res_begin) res_buf = cur;
     // output buffer: any workspace buffer that is neither the input nor the live residual
@@ -328,11 +368,14 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
           break;
         }
       a.out = h->act[ob];
-      a.out_mode = IO_ACT;
+      a.out_mode = pair16 ? IO_ACT16 : IO_ACT;
+      a.out_lo_off = (long long)n * a.hout * a.wout * a.cout;
     }
     if (d.res_end) {
       if (res_buf < 0) return fail(h, TIC_ERR_INVALID, "res_end without res_begin at layer %d", i);
       a.res = h->act[res_buf];
+      a.res16 = pair16 ? 1 : 0;
+      a.res_lo_off = (long long)n * a.hout * a.wout * a.cout;
     }
     int rc;
     tic_codec::ProfRec pr{gi, i, nullptr, nullptr};
@@ -341,7 +384,11 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
       cudaEventCreate(&pr.e1);
       cudaEventRecord(pr.e0, h->stream);
     }
-    if (h->mode != TIC_COMPUTE_FP32 && umma_supported(a, d.kind, d.stride)) {
+    if (pair16 && u16_supported(a, d.kind, d.stride)) {
+      int nl = 0;
+      rc = launch_u16(h->stream, a, d.kind, d.stride, ly.w, &ly.uw16, h->num_sms, &h->err, &nl);
+      h->launches += nl;
+    } else if (h->mode != TIC_COMPUTE_FP32 && !pair16 && umma_supported(a, d.kind, d.stride)) {
       int nl = 0;
       rc = launch_umma(h->stream, a, d.kind, d.stride, ly.w, &ly.uw, h->mode == TIC_COMPUTE_TENSOR_3XTF32,
                        h->num_sms, &h->err, &nl);
@@ -527,6 +574,7 @@ void tic_destroy(tic_codec* h) {
       if (l.w) cudaFree(l.w);
       if (l.b) cudaFree(l.b);
       l.uw.release();
+      l.uw16.release();
     }
     if (h->g[gi].d_normlut) cudaFree(h->g[gi].d_normlut);
   }
@@ -564,7 +612,7 @@ int tic_set_stream(tic_codec* h, void* cuda_stream) {
 
 int tic_set_compute_mode(tic_codec* h, int mode) {
   if (!h) return TIC_ERR_INVALID;
-  if (mode < TIC_COMPUTE_FP32 || mode > TIC_COMPUTE_TENSOR_TF32) return fail(h, TIC_ERR_INVALID, "unknown compute mode %d", mode);
+  if (mode < TIC_COMPUTE_FP32 || mode > TIC_COMPUTE_TENSOR_F16X3) return fail(h, TIC_ERR_INVALID, "unknown compute mode %d", mode);
   h->mode = mode;
   return TIC_OK;
 }
@@ -606,6 +654,7 @@ int tic_set_graph(tic_codec* h, int graph, const tic_layer_desc* layers, int n_l
     if (l.w) cudaFree(l.w);
     if (l.b) cudaFree(l.b);
     l.uw.release();
+    l.uw16.release();
   }
   g.layers.assign(n_layers, Layer());
   for (int i = 0; i < n_layers; ++i) {
@@ -639,6 +688,7 @@ int tic_load_weights(tic_codec* h, int graph, int layer, const float* kernel, co
   TIC_CUDA(h, cudaMemcpy(l.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
   TIC_CUDA(h, cudaMemcpy(l.b, bias, (size_t)cout * sizeof(float), cudaMemcpyHostToDevice));
   l.uw.release();
+  l.uw16.release();
   l.loaded = true;
   return TIC_OK;
 }

@@ -1,6 +1,7 @@
 // Shared device-side types for the codec kernels: fused-I/O geometry (crop / stitch by index
 // arithmetic), per-layer launch arguments, first-layer prologue and last-layer epilogue helpers.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/tic_math.h"
@@ -16,7 +17,8 @@ enum IoMode : int {
   IO_QUANT_U8 = 4,     // out: sigmoid*(q-1), round -> u8 symbols + histogram              (model_0/model.py:137-138)
   IO_QUANT_F32 = 5,    // out: same, stored as integer-valued f32 (what sess.run returns)
   IO_DENORM_F32 = 6,   // out: clip(y*std+mean,0,255) f32 through Geo                      (model_0/model.py:251,259)
-  IO_DENORM_U8 = 7     // out: same then np.around -> u8 through Geo                       (decode.py:249)
+  IO_DENORM_U8 = 7,    // out: same then np.around -> u8 through Geo                       (decode.py:249)
+  IO_ACT16 = 8         // fp16 pair planes (hi, lo' = (x - hi) * 2048) of an NHWC activation (tic_umma16.cuh)
 };
 
 // Patch <-> image geometry.  A "patch array" [n,P,P,3] is the degenerate case
@@ -80,8 +82,21 @@ struct LayerArgs {
   float mean[3], stdv[3];
   int q;
   unsigned long long* hist;  // [256] symbol counts (IO_QUANT_*)
+  // IO_ACT16 tensors: `in` / `out` / `res` point at the hi plane, the lo' plane starts *_lo_off halves later
+  long long in_lo_off, out_lo_off, res_lo_off;
+  int res16;             // residual source is a pair-plane tensor
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act ? fmaxf(v, 0.0f) : v; }
+
+// fp16 pair representation of an fp32 value: x ~= hi + lo' / 2048 (22 significant bits; the parts do not
+// overlap, so the re-join is exact in fp32).  |x| must stay below 65504 (fp16 range).
+__device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(__fmul_rn(__fsub_rn(v, __half2float(hi)), 2048.0f));
+}
+__device__ __forceinline__ float join16(__half hi, __half lo) {
+  return __fmaf_rn(__half2float(lo), 1.0f / 2048.0f, __half2float(hi));
+}
 
 }  // namespace tic

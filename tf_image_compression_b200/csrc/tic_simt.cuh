@@ -42,6 +42,11 @@ __device__ __forceinline__ float fetch_input(const LayerArgs& a, int n, int Y, i
       float v = reinterpret_cast<const float*>(a.in)[off * 3 + c];
       return tic_normalize(v, a.mean[c], a.stdv[c]);
     }
+    case IO_ACT16: {
+      const long long off = (((long long)n * a.hin + Y) * a.win + X) * a.cin + c;
+      const __half* hp = reinterpret_cast<const __half*>(a.in);
+      return join16(hp[off], hp[off + a.in_lo_off]);
+    }
     case IO_U8_SYMLUT: {
       unsigned v = reinterpret_cast<const uint8_t*>(
           a.in)[((((long long)a.geo.n0 + n) * a.hin + Y) * a.win + X) * a.cin + c];
@@ -109,6 +114,31 @@ __device__ __forceinline__ void stage_tiles(const LayerArgs& a, const SmemPlan& 
       d[2 * sp.cstr] = val.z;
       d[3 * sp.cstr] = val.w;
     }
+  } else if (a.in_mode == IO_ACT16 && (a.cin & 3) == 0) {
+    const __half* in = reinterpret_cast<const __half*>(a.in);
+    for (int u = tid; u < npix * (kIcc / 4); u += kThreads) {
+      int c4 = u % (kIcc / 4);
+      int pix = u / (kIcc / 4);
+      int ix = pix % sp.iw;
+      int r = pix / sp.iw;
+      int iy = r % sp.ih;
+      int pp = r / sp.ih;
+      int n = pg * a.TP + pp, Y = y_in0 + iy, X = x_in0 + ix, c = ic0 + c4 * 4;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n < a.n && Y >= 0 && Y < a.hin && X >= 0 && X < a.win && c < a.cin) {
+        const __half* q = in + (((long long)n * a.hin + Y) * a.win + X) * a.cin + c;
+        const uint2 qh = __ldg(reinterpret_cast<const uint2*>(q));
+        const uint2 ql = __ldg(reinterpret_cast<const uint2*>(q + a.in_lo_off));
+        const __half* h4 = reinterpret_cast<const __half*>(&qh);
+        const __half* l4 = reinterpret_cast<const __half*>(&ql);
+        val = make_float4(join16(h4[0], l4[0]), join16(h4[1], l4[1]), join16(h4[2], l4[2]), join16(h4[3], l4[3]));
+      }
+      float* d = s_in + pp * sp.pstr + (c4 * 4) * sp.cstr + iy * sp.iwp + ix;
+      d[0] = val.x;
+      d[sp.cstr] = val.y;
+      d[2 * sp.cstr] = val.z;
+      d[3 * sp.cstr] = val.w;
+    }
   } else {
     for (int u = tid; u < npix * kIcc; u += kThreads) {
       int c = u % kIcc;
@@ -169,6 +199,29 @@ __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, in
 #pragma unroll
         for (int i = 0; i < NV; ++i)
           if (oc + i < a.cout) o[i] = v[i];
+      }
+      break;
+    }
+    case IO_ACT16: {
+      __half* oh = reinterpret_cast<__half*>(a.out) + pix * a.cout + oc;
+      __half* ol = oh + a.out_lo_off;
+      if ((a.cout & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i += 4) {
+          if (oc + i < a.cout) {
+            uint2 qh, ql;
+            __half* h4 = reinterpret_cast<__half*>(&qh);
+            __half* l4 = reinterpret_cast<__half*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split16(v[i + e], h4[e], l4[e]);
+            *reinterpret_cast<uint2*>(oh + i) = qh;
+            *reinterpret_cast<uint2*>(ol + i) = ql;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (oc + i < a.cout) split16(v[i], oh[i], ol[i]);
       }
       break;
     }
@@ -320,10 +373,18 @@ __global__ void __launch_bounds__(kThreads) conv3x3_simt_kernel(const LayerArgs 
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = apply_act(__fadd_rn(acc[j][i], b[i]), a.act);
       if (a.res) {
-        const float* rp = a.res + (((long long)n * a.hout + y) * a.wout + xo) * a.cout + oc;
+        const long long ro = (((long long)n * a.hout + y) * a.wout + xo) * a.cout + oc;
+        if (a.res16) {
+          const __half* rh = reinterpret_cast<const __half*>(a.res) + ro;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (oc + i < a.cout) o[i] = __fadd_rn(__ldg(rp + i), o[i]);
+          for (int i = 0; i < 8; ++i)
+            if (oc + i < a.cout) o[i] = __fadd_rn(join16(rh[i], rh[i + a.res_lo_off]), o[i]);
+        } else {
+          const float* rp = a.res + ro;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (oc + i < a.cout) o[i] = __fadd_rn(__ldg(rp + i), o[i]);
+        }
       }
       store_pixel<8>(a, n, y, xo, oc, o, s_hist, h_ones, h_valid);
     }

@@ -1,0 +1,647 @@
+// tcgen05 / TMEM / TMA implicit-GEMM kernels, fp16-pair operands (compute mode TIC_COMPUTE_TENSOR_F16X3):
+// the 3x3 conv (stride 1 and 2) and the stride-2 transposed conv of the codec
+// (basic_block/basic_block.py:27-71) with fp32-class accuracy on the fp16 tensor pipe.
+//
+// Why fp16 pairs (measured, profiles/r1b_umma_f16_probe.log): one tcgen05.mma with M = 128 and a 32-byte
+// K slice costs 85..113 cycles for N <= 128 whatever its kind, so the cost of a layer is its INSTRUCTION
+// count.  kind::f16 covers 16 channels per instruction (kind::tf32: 8) and fp16 has the same 11-bit
+// significand as tf32, so the error-compensated three-product scheme keeps its accuracy at half the
+// instructions:   x = hi + lo' / 2048,  hi = rn_f16(x),  lo' = rn_f16((x - hi) * 2048)
+//   D_main += A_hi * W_hi            D_lo += A_hi * W_lo' + A_lo' * W_hi          out = D_main + D_lo / 2048
+// The first two products share their A operand, so they are ONE instruction with N = 2 * cout over the
+// stacked weight tile [W_hi ; W_lo'] writing the adjacent accumulator pair (D_main | D_lo).
+//
+// Activations live in HBM pre-split: two fp16 planes (hi, lo') of the NHWC tensor, 4 bytes per element like
+// fp32.  The producing epilogue splits once per element; consumers TMA the planes straight into
+// MMA-ready swizzled tiles (no converter warps, no shared-memory round trip).
+//
+// Operand staging ("one box, nine taps", probe F2): per K-block ONE TMA box per plane covers the whole
+// halo (stride 1: 10 columns x (rows + 2); the box dims are ordered (C, W, N, H)).  A filter tap is a
+// descriptor start offset of (kh * box_columns + kw) rows — not a multiple of the swizzle atom, which is
+// fine because the swizzle XOR is a function of the absolute shared-memory address — and the 8-pixel row
+// groups sit box_columns rows apart (descriptor SBO).  Stride 2 uses a 5-D map ((w parity, C), W/2,
+// h parity, N, H/2); the transposed conv walks INPUT pixels and feeds four sub-pixel phase accumulators.
+// Weights ([W_hi ; W_lo'] per tap, pre-swizzled) are loaded ONCE per CTA and stay resident; layers whose
+// weights do not fit run as output-channel slices.
+//
+// TMEM: per tile `nsplit` (D_main | D_lo) pairs — the tensor core truncates when it adds into the fp32
+// accumulator (tests/probe/umma_accum_probe.cu), so the K steps rotate over nsplit accumulators that the
+// epilogue sums with round-to-nearest adds — and two tile buffers so the epilogue of tile i overlaps the
+// MMAs of tile i+1.
+// Warp roles (256 threads): 0 TMA producer, 1 MMA issuer (elect.sync: a plain `if (lane == 0)` region makes
+// ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop), 2 TMEM allocator, 4-7 epilogue.
+#pragma once
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_fp16.h>
+
+#include <string>
+
+#include "tic_common.cuh"
+#include "tic_ptx.cuh"
+#include "tic_simt.cuh"
+
+namespace tic {
+
+enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2 };
+
+constexpr int kU16Threads = 256;
+constexpr int kU16MaxSlots = 6;
+
+struct U16Params {
+  int mode;
+  int n;                 // patches
+  int Ht, Wt;            // tile-space map (S1/S2: output map, DECONV: input map)
+  int bn, bh;            // patches per tile (1 | 2), map rows per tile per patch (16 | 8)
+  int tiles_x, tiles_y;
+  long long num_tiles;
+  int KB;                // K-blocks (input-channel chunks of kc)
+  int kc;                // channels per K-block
+  int ksteps;            // MMAs (K = 16) per tap per K-block
+  int npad;              // output channels of this launch rounded up to 16 (MMA N = npad or 2 * npad)
+  int oc0;               // first output channel of this launch (slice)
+  int nsplit;            // conv: accumulator pairs the K steps rotate over; deconv: 1
+  int nbuf;              // TMEM tile buffers (1 | 2)
+  uint32_t acc_cols;     // TMEM columns per tile buffer
+  uint32_t a_layout;     // descriptor layout code of the A rows (2 = SW128, 4 = SW64, 6 = SW32)
+  uint32_t w_layout;     // ... of the weight rows
+  uint32_t sbo;          // A: bytes between 8-row groups
+  uint32_t w_sbo;        // W: 8 * weight row bytes
+  uint32_t a_off[9];     // per tap (kh * 3 + kw): start offset inside a plane slot
+  uint32_t box_bytes;    // one TMA box
+  uint32_t box_stride;   // box_bytes rounded up to 1024 (second parity box of a stride-2 slot)
+  int nbox;              // boxes per plane (stride 2 with 64-channel K-blocks: one per w parity)
+  uint32_t slot_bytes;
+  int S;                 // plane slots in the ring
+  uint32_t tap_bytes;    // [W_hi ; W_lo'] of one tap of one K-block
+  uint32_t w_bytes;      // KB * 9 * tap_bytes
+  const uint8_t* wimg;
+  long long in_lo_off;   // elements between the hi and lo' planes of the input (unused by the kernel: second tensor map)
+};
+
+struct U16WeightSlice {
+  uint8_t* img = nullptr;
+  size_t bytes = 0;
+  int mode = -1, npad = 0, oc0 = -1;
+  void release() {
+    if (img) cudaFree(img);
+    img = nullptr;
+    bytes = 0;
+    mode = -1;
+  }
+};
+struct U16Weights {
+  U16WeightSlice slice[16];
+  void release() {
+    for (auto& sl : slice) sl.release();
+  }
+};
+
+__host__ __device__ inline uint32_t u16_swz(uint32_t off, uint32_t rowbytes) {
+  const uint32_t mask = rowbytes >= 128 ? 7u : rowbytes == 64 ? 3u : 1u;
+  return off ^ (((off >> 7) & mask) << 4);
+}
+__host__ __device__ inline uint32_t u16_layout_code(uint32_t rowbytes) { return rowbytes >= 128 ? 2u : rowbytes == 64 ? 4u : 6u; }
+
+// device [9][cin][cout] fp32 -> [kb][tap][hi rows npad | lo' rows npad][kc] fp16, swizzled rows of kc * 2 bytes
+__global__ void u16_build_weights_kernel(const float* __restrict__ w, int cin, int cout, int oc0, int cs, int npad, int kc,
+                                         int KB, uint8_t* __restrict__ img) {
+  const uint32_t wrow = (uint32_t)kc * 2u;
+  const uint32_t tap_bytes = 2u * npad * wrow;
+  const long long total = (long long)KB * 9 * npad * kc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kc);
+    const int oc = (int)((i / kc) % npad);
+    const int t = (int)(i / ((long long)kc * npad));
+    const int kb = t / 9, tap = t % 9;
+    const int ic = kb * kc + k;
+    const float v = (oc < cs && ic < cin) ? w[((size_t)tap * cin + ic) * cout + oc0 + oc] : 0.f;
+    __half hi, lo;
+    split16(v, hi, lo);
+    uint8_t* base = img + (size_t)t * tap_bytes;
+    *reinterpret_cast<__half*>(base + u16_swz((uint32_t)oc * wrow + k * 2, wrow)) = hi;
+    *reinterpret_cast<__half*>(base + u16_swz((uint32_t)(npad + oc) * wrow + k * 2, wrow)) = lo;
+  }
+}
+
+// fp32 NHWC -> fp16 pair planes (caller-provided f32 activations: tic_run_layers)
+__global__ void u16_split_f32_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    __half h, l;
+    split16(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+// u8 symbols -> inverse-sigmoid LUT (model_0/model.py:153) -> fp16 pair planes
+__global__ void u16_split_symlut_kernel(const uint8_t* __restrict__ sym, const float* __restrict__ lut, __half* __restrict__ hi,
+                                        __half* __restrict__ lo, long long count) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    __half h, l;
+    split16(__ldg(lut + sym[i]), h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+struct U16SmemBars {
+  uint64_t w_full;
+  uint64_t full[kU16MaxSlots], empty[kU16MaxSlots];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint64_t u16_desc(uint32_t lo32, uint32_t hi32) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo32), "r"(hi32));
+  return d;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kU16Threads, 1)
+u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const U16Params p,
+                const LayerArgs a) {
+  const int NPAD = p.npad;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w = smem;                                             // resident weights
+  uint8_t* s_a = smem + ((p.w_bytes + 1023u) & ~1023u);            // S plane slots
+  U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_a + (size_t)p.S * p.slot_bytes);
+  __shared__ unsigned s_hist[256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    ptx::mbar_init(&bars->w_full, 1);
+    for (int i = 0; i < p.S; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->acc_full[i], 1);
+      ptx::mbar_init(&bars->acc_empty[i], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  for (int i = tid; i < 256; i += kU16Threads) s_hist[i] = 0;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===== TMA producer: resident weights once, then per tile and K-block the hi plane and the lo' plane =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tm_hi);
+      ptx::prefetch_tmap(&tm_lo);
+      ptx::mbar_expect_tx(&bars->w_full, p.w_bytes);
+      for (uint32_t off = 0; off < p.w_bytes; off += p.tap_bytes)
+        ptx::bulk_load(s_w + off, p.wimg + off, p.tap_bytes, &bars->w_full);
+    }
+    __syncwarp();
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long long tt = tile;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n0 = (int)(tt / p.tiles_y) * p.bn;
+      const int x0 = tx * 8, y0 = ty * p.bh;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        for (int plane = 0; plane < 2; ++plane, ++it) {
+          const int s = it % p.S;
+          ptx::mbar_wait(&bars->empty[s], ((it / p.S) & 1) ^ 1);
+          if (ptx::elect_one()) {
+            const CUtensorMap* tm = plane ? &tm_lo : &tm_hi;
+            uint8_t* dst = s_a + (size_t)s * p.slot_bytes;
+            ptx::mbar_expect_tx(&bars->full[s], p.box_bytes * (uint32_t)p.nbox);
+            if (MODE == U16_S2) {
+              if (p.nbox == 1) {
+                ptx::tma_load_5d(dst, tm, &bars->full[s], kb * p.kc, x0, 0, n0, y0);  // row = both w parities (kc == cin)
+              } else {
+                ptx::tma_load_5d(dst, tm, &bars->full[s], kb * p.kc, x0, 0, n0, y0);
+                ptx::tma_load_5d(dst + p.box_stride, tm, &bars->full[s], a.cin + kb * p.kc, x0, 0, n0, y0);
+              }
+            } else {
+              ptx::tma_load_4d(dst, tm, &bars->full[s], kb * p.kc, x0 - 1, n0, y0 - 1);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the whole warp walks the loop, one elected lane issues =====
+    const uint32_t idesc_st = ptx::make_idesc_f16(128, 2 * NPAD);  // A_hi x [W_hi ; W_lo'] -> (D_main | D_lo)
+    const uint32_t idesc_lo = ptx::make_idesc_f16(128, NPAD);      // A_lo' x W_hi -> D_lo
+    const uint32_t a_hi32 = (p.sbo >> 4) | (1u << 14) | (p.a_layout << 29);
+    const uint32_t w_hi32 = (p.w_sbo >> 4) | (1u << 14) | (p.w_layout << 29);
+    const uint32_t tapw = p.tap_bytes >> 4;
+    ptx::mbar_wait(&bars->w_full, 0);
+    uint32_t it = 0, ti = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
+      const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+      ptx::mbar_wait(&bars->acc_empty[b], (use & 1) ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t dbase = tmem_base + b * p.acc_cols;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        for (int plane = 0; plane < 2; ++plane, ++it) {
+          const int s = it % p.S;
+          ptx::mbar_wait(&bars->full[s], (it / p.S) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
+            const uint32_t wbase = (ptx::smem_u32(s_w + (size_t)kb * 9 * p.tap_bytes) >> 4) | (1u << 16);
+            const uint32_t idesc = plane ? idesc_lo : idesc_st;
+            const uint32_t dplane = dbase + (plane ? (uint32_t)NPAD : 0u);
+            uint32_t step = (uint32_t)kb * 9u * (uint32_t)p.ksteps;
+#pragma unroll 1
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t ad = abase + (p.a_off[tap] >> 4);
+              const uint32_t bd = wbase + (uint32_t)tap * tapw;
+              uint32_t acc, fresh;
+              if (MODE == U16_DECONV) {
+                const int kh = tap / 3, kw = tap - kh * 3;
+                acc = (uint32_t)((kh == 1) * 2 + (kw == 1));
+                fresh = (kb == 0 && plane == 0 && (tap == 0 || tap == 1 || tap == 3 || tap == 4)) ? 1u : 0u;
+              } else {
+                acc = 0;
+                fresh = 0;
+              }
+              for (int ks = 0; ks < p.ksteps; ++ks, ++step) {
+                uint32_t d, accumulate;
+                if (MODE == U16_DECONV) {
+                  d = dplane + acc * 2u * (uint32_t)NPAD;
+                  accumulate = (fresh && ks == 0) ? 0u : 1u;
+                } else {
+                  const uint32_t sp = step % (uint32_t)p.nsplit;
+                  d = dplane + sp * 2u * (uint32_t)NPAD;
+                  accumulate = (plane == 0 && step < (uint32_t)p.nsplit) ? 0u : 1u;
+                }
+                ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
+              }
+            }
+          }
+          __syncwarp();
+          if (ptx::elect_one()) ptx::tc_commit(&bars->empty[s]);
+          __syncwarp();
+        }
+      }
+      if (ptx::elect_one()) ptx::tc_commit(&bars->acc_full[b]);
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> registers -> sum splits / bias / act / residual -> pair planes | f32 | symbols =====
+    const int q4 = warp & 3;            // TMEM lane quadrant this warp may access
+    const int m = q4 * 32 + lane;       // tile row = pixel
+    const int grp = m >> 3, xx = m & 7;
+    const int hh = grp / p.bn, nb = grp % p.bn;
+    const int phases = MODE == U16_DECONV ? 4 : 1;
+    int h_ones = 0, h_valid = 0;
+    uint32_t ti = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
+      const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+      ptx::mbar_wait(&bars->acc_full[b], use & 1);
+      ptx::tc_fence_after();
+      long long tt = tile;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
+      const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
+      const bool valid = n < p.n;
+      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
+      for (int ph = 0; ph < phases; ++ph) {
+        const int y = MODE == U16_DECONV ? 2 * yt + (ph >> 1) : yt;
+        const int x = MODE == U16_DECONV ? 2 * xt + (ph & 1) : xt;
+        for (int c = 0; c < NPAD; c += 16) {
+          float v[16];
+          if (MODE == U16_DECONV || p.nsplit == 1) {
+            float u[16];
+            const uint32_t t0 = tbuf + (uint32_t)ph * 2u * NPAD + c;
+            ptx::tmem_ld16_nowait(t0 + NPAD, u);
+            ptx::tmem_ld16_nowait(t0, v);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(u[i], 1.0f / 2048.0f, v[i]);
+          } else {
+            // lo' accumulators first (small), then the main accumulators, round-to-nearest adds
+            float lo[16];
+            ptx::tmem_ld16_nowait(tbuf + NPAD + c, lo);
+            ptx::tmem_ld16_nowait(tbuf + c, v);
+            ptx::tmem_ld_wait();
+            for (int j = 1; j < p.nsplit; ++j) {
+              float u[16], w[16];
+              ptx::tmem_ld16_nowait(tbuf + (uint32_t)j * 2u * NPAD + NPAD + c, u);
+              ptx::tmem_ld16_nowait(tbuf + (uint32_t)j * 2u * NPAD + c, w);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                lo[i] = __fadd_rn(lo[i], u[i]);
+                v[i] = __fadd_rn(v[i], w[i]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(lo[i], 1.0f / 2048.0f, v[i]);
+          }
+          const int cl = c;            // channel inside the slice
+          const int oc = p.oc0 + cl;   // channel of the layer
+          if (valid && oc < a.cout) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float bb = (oc + i < a.cout) ? __ldg(a.bias + oc + i) : 0.f;
+              v[i] = apply_act(__fadd_rn(v[i], bb), a.act);
+            }
+            const long long pix = ((long long)n * a.hout + y) * a.wout + x;
+            if (a.res) {
+              if (a.res16) {
+                const __half* rh = reinterpret_cast<const __half*>(a.res) + pix * a.cout + oc;
+                const __half* rl = rh + a.res_lo_off;
+#pragma unroll
+                for (int i = 0; i < 16; i += 8) {
+                  if (oc + i < a.cout) {
+                    const uint4 qh = __ldg(reinterpret_cast<const uint4*>(rh + i));
+                    const uint4 ql = __ldg(reinterpret_cast<const uint4*>(rl + i));
+                    const __half* ph8 = reinterpret_cast<const __half*>(&qh);
+                    const __half* pl8 = reinterpret_cast<const __half*>(&ql);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[i + e] = __fadd_rn(join16(ph8[e], pl8[e]), v[i + e]);
+                  }
+                }
+              } else {
+                const float* rp = a.res + pix * a.cout + oc;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  if (oc + i < a.cout) {
+                    const float4 r = __ldg(reinterpret_cast<const float4*>(rp + i));
+                    v[i] = __fadd_rn(r.x, v[i]);
+                    v[i + 1] = __fadd_rn(r.y, v[i + 1]);
+                    v[i + 2] = __fadd_rn(r.z, v[i + 2]);
+                    v[i + 3] = __fadd_rn(r.w, v[i + 3]);
+                  }
+                }
+              }
+            }
+            if (a.out_mode == IO_ACT16) {
+              __half* oh = reinterpret_cast<__half*>(a.out) + pix * a.cout + oc;
+              __half* ol = oh + a.out_lo_off;
+#pragma unroll
+              for (int i = 0; i < 16; i += 8) {
+                if (oc + i < a.cout) {
+                  uint4 qh, ql;
+                  __half* ph8 = reinterpret_cast<__half*>(&qh);
+                  __half* pl8 = reinterpret_cast<__half*>(&ql);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) split16(v[i + e], ph8[e], pl8[e]);
+                  *reinterpret_cast<uint4*>(oh + i) = qh;
+                  *reinterpret_cast<uint4*>(ol + i) = ql;
+                }
+              }
+            } else {
+              store_pixel<16>(a, n, y, x, oc, v, s_hist, h_ones, h_valid);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
+    }
+    // symbol histogram (quantising layers): reduce the 4 epilogue warps through shared memory
+    if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
+      if (a.q == 2) {
+        h_ones = __reduce_add_sync(0xffffffffu, h_ones);
+        h_valid = __reduce_add_sync(0xffffffffu, h_valid);
+        if (lane == 0) {
+          if (h_ones) atomicAdd(&s_hist[1], (unsigned)h_ones);
+          if (h_valid - h_ones) atomicAdd(&s_hist[0], (unsigned)(h_valid - h_ones));
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      for (int i = tid - 128; i < a.q; i += 128)
+        if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+inline int u16_mode_of(int kind, int stride) { return kind == 1 ? U16_DECONV : (stride == 2 ? U16_S2 : U16_S1); }
+
+// Which layers the fp16-pair tensor path takes (input must already be pair planes).
+inline bool u16_supported(const LayerArgs& a, int kind, int stride) {
+  if (a.in_mode != IO_ACT16) return false;
+  if (!(a.cin == 16 || a.cin == 32 || (a.cin % 64 == 0 && a.cin <= 512))) return false;
+  if (a.cout < 16) return false;  // 3-channel output layers: CUDA-core kernel
+  const int mode = u16_mode_of(kind, stride);
+  const int Ht = mode == U16_DECONV ? a.hin : a.hout, Wt = mode == U16_DECONV ? a.win : a.wout;
+  if (Wt % 8 != 0) return false;
+  if (!(Ht == 8 || Ht % 16 == 0)) return false;
+  if (mode == U16_S2 && (a.hin != 2 * a.hout || a.win != 2 * a.wout)) return false;
+  if ((a.out_mode == IO_ACT16 || a.res16) && (a.cout % 8) != 0) return false;
+  if ((a.out_mode == IO_ACT || (a.res && !a.res16)) && (a.cout % 4) != 0) return false;
+  if (a.out_mode == IO_DENORM_F32 || a.out_mode == IO_DENORM_U8) return false;
+  return true;
+}
+
+template <int MODE>
+inline cudaError_t u16_launch_t(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
+                                const LayerArgs& a, int grid, size_t smem) {
+  auto k = u16_conv_kernel<MODE>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  k<<<grid, kU16Threads, smem, stream>>>(th, tl, p, a);
+  return cudaGetLastError();
+}
+
+struct U16Plan {
+  int cs;      // output channels per slice
+  U16Params p;
+  size_t smem;
+};
+
+// Geometry + shared-memory plan for one slice width; returns false if it does not fit.
+inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out) {
+  U16Params p{};
+  p.mode = u16_mode_of(kind, stride);
+  p.n = a.n;
+  p.Ht = p.mode == U16_DECONV ? a.hin : a.hout;
+  p.Wt = p.mode == U16_DECONV ? a.win : a.wout;
+  p.bn = p.Ht == 8 ? 2 : 1;
+  p.bh = p.Ht == 8 ? 8 : 16;
+  p.tiles_x = p.Wt / 8;
+  p.tiles_y = p.Ht / p.bh;
+  p.num_tiles = (long long)p.tiles_x * p.tiles_y * ((a.n + p.bn - 1) / p.bn);
+  p.kc = std::min(a.cin, 64);
+  p.KB = a.cin / p.kc;
+  p.ksteps = p.kc / 16;
+  p.npad = (cs + 15) / 16 * 16;
+  const uint32_t wrow = (uint32_t)p.kc * 2u;
+  uint32_t arow = wrow;
+  int box_rows, bw;
+  if (p.mode == U16_S1) {
+    bw = 10;
+    box_rows = bw * p.bn * (p.bh + 2);
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) p.a_off[kh * 3 + kw] = (uint32_t)((kh * p.bn) * bw + kw) * arow;
+    p.sbo = (uint32_t)bw * arow;
+    p.nbox = 1;
+  } else if (p.mode == U16_DECONV) {
+    bw = 9;
+    box_rows = bw * p.bn * (p.bh + 1);
+    // tap (kh, kw) reads input row a - (kh == 2), column b - (kw == 2); box row 0 / column 0 = a-1 / b-1
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int dy = kh == 2 ? 0 : 1, dx = kw == 2 ? 0 : 1;
+        p.a_off[kh * 3 + kw] = (uint32_t)((dy * p.bn) * bw + dx) * arow;
+      }
+    p.sbo = (uint32_t)bw * arow;
+    p.nbox = 1;
+  } else {
+    bw = 9;
+    const bool both = 2u * wrow <= 128u && p.KB == 1;  // a row holds both w parities of one W/2 position
+    arow = both ? 2u * wrow : wrow;
+    p.nbox = both ? 1 : 2;
+    box_rows = bw * 2 * p.bn * (p.bh + 1);
+    // input (2 oy + kh, 2 ox + kw): kh -> (h parity, h2 shift) = (0,0) (1,0) (0,1); same for kw
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        uint32_t rows = (uint32_t)((kh == 1 ? bw : 0) + (kh == 2 ? 2 * p.bn * bw : 0) + (kw == 2 ? 1 : 0));
+        uint32_t off = rows * arow;
+        if (kw == 1) off += both ? wrow : 0u;
+        p.a_off[kh * 3 + kw] = off;  // second-parity box offset added below (needs box_stride)
+      }
+    p.sbo = (uint32_t)(2 * bw) * arow;
+  }
+  p.a_layout = u16_layout_code(arow);
+  p.w_layout = u16_layout_code(wrow);
+  p.w_sbo = 8u * wrow;
+  p.box_bytes = (uint32_t)box_rows * arow;
+  p.box_stride = (p.box_bytes + 1023u) & ~1023u;
+  if (p.mode == U16_S2 && p.nbox == 2)
+    for (int kh = 0; kh < 3; ++kh) p.a_off[kh * 3 + 1] += p.box_stride;
+  p.slot_bytes = p.box_stride * (uint32_t)p.nbox;
+  p.tap_bytes = 2u * (uint32_t)p.npad * wrow;
+  p.w_bytes = (uint32_t)p.KB * 9u * p.tap_bytes;
+  // TMEM: conv nsplit pairs x 2 buffers; deconv 4 phase pairs
+  const int pair = 2 * p.npad;
+  if (p.mode == U16_DECONV) {
+    p.nsplit = 1;
+    p.acc_cols = 4u * pair;
+    if (p.acc_cols > 512) return false;
+    p.nbuf = p.acc_cols * 2 <= 512 ? 2 : 1;
+  } else {
+    if (pair > 512) return false;
+    p.nbuf = pair * 2 <= 512 ? 2 : 1;
+    p.nsplit = std::max(1, std::min(4, (512 / p.nbuf) / pair));
+    p.nsplit = std::min(p.nsplit, std::max(1, p.KB * 9 * p.ksteps / 4));
+    p.acc_cols = (uint32_t)(p.nsplit * pair);
+  }
+  if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
+  const size_t budget = 227 * 1024 - 1024 /* static histogram */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
+  const size_t wres = (p.w_bytes + 1023u) & ~1023u;
+  if (wres + 2 * (size_t)p.slot_bytes > budget) return false;
+  p.S = (int)std::min<size_t>(kU16MaxSlots, (budget - wres) / p.slot_bytes);
+  out->cs = cs;
+  out->p = p;
+  out->smem = wres + (size_t)p.S * p.slot_bytes + sizeof(U16SmemBars) + 1024;
+  return true;
+}
+
+inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int stride, const float* w_dev, U16Weights* uw,
+                      int num_sms, std::string* err, int* launches) {
+  auto fail = [&](const std::string& what, int code) {
+    if (err) *err = what;
+    return code;
+  };
+  auto encode = umma_encode_fn();
+  if (!encode) return fail("cuTensorMapEncodeTiled is unavailable (driver too old?)", -2);
+  // widest output-channel slice whose weights stay resident
+  U16Plan plan{};
+  int cs = std::min(a.cout, 128);
+  cs = (cs + 15) / 16 * 16;
+  bool ok = false;
+  for (; cs >= 16; cs -= 16)
+    if ((ok = u16_plan(a, kind, stride, std::min(cs, a.cout), &plan))) break;
+  if (!ok) return fail("layer does not fit the fp16-pair tensor path", -5);
+  cs = plan.cs;
+
+  // tensor maps over the two planes of the input activation [n, hin, win, cin] fp16
+  CUtensorMap tm[2];
+  const U16Params& p0 = plan.p;
+  const cuuint64_t C = a.cin, W = a.win, H = a.hin, N = a.n;
+  for (int pl = 0; pl < 2; ++pl) {
+    void* base = const_cast<__half*>(reinterpret_cast<const __half*>(a.in) + (pl ? a.in_lo_off : 0));
+    CUresult r;
+    const CUtensorMapSwizzle sw = p0.a_layout == 2 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : p0.a_layout == 4 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    if (p0.mode != U16_S2) {
+      cuuint64_t dims[4] = {C, W, N, H};
+      cuuint64_t strides[3] = {C * 2, H * W * C * 2, W * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)p0.kc, (cuuint32_t)(p0.mode == U16_S1 ? 10 : 9), (cuuint32_t)p0.bn,
+                           (cuuint32_t)(p0.bh + (p0.mode == U16_S1 ? 2 : 1))};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      r = encode(&tm[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[5] = {2 * C, W / 2, 2, N, H / 2};
+      cuuint64_t strides[4] = {2 * C * 2, W * C * 2, H * W * C * 2, 2 * W * C * 2};
+      cuuint32_t box[5] = {(cuuint32_t)(p0.nbox == 1 ? 2 * p0.kc : p0.kc), 9, 2, (cuuint32_t)p0.bn, (cuuint32_t)(p0.bh + 1)};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      r = encode(&tm[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")", -2);
+  }
+
+  int si = 0;
+  for (int oc0 = 0; oc0 < a.cout; oc0 += cs, ++si) {
+    if (si >= 16) return fail("too many output-channel slices", -5);
+    const int csl = std::min(cs, a.cout - oc0);
+    U16Plan pl{};
+    if (!u16_plan(a, kind, stride, csl, &pl)) return fail("slice plan failed", -5);
+    U16Params p = pl.p;
+    p.oc0 = oc0;
+    U16WeightSlice* ws = &uw->slice[si];
+    if (!ws->img || ws->bytes != p.w_bytes || ws->mode != p.mode || ws->npad != p.npad || ws->oc0 != oc0) {
+      ws->release();
+      if (cudaMalloc(&ws->img, p.w_bytes) != cudaSuccess) return fail("cudaMalloc for weight images failed", -4);
+      ws->bytes = p.w_bytes;
+      ws->mode = p.mode;
+      ws->npad = p.npad;
+      ws->oc0 = oc0;
+      u16_build_weights_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.kc, p.KB, ws->img);
+      if (cudaGetLastError() != cudaSuccess) return fail("weight image kernel failed", -2);
+    }
+    p.wimg = ws->img;
+    const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
+    cudaError_t e;
+    if (p.mode == U16_S1)
+      e = u16_launch_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    else if (p.mode == U16_S2)
+      e = u16_launch_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    else
+      e = u16_launch_t<U16_DECONV>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    if (e != cudaSuccess) return fail(std::string("fp16-pair tensor launch failed: ") + cudaGetErrorString(e), -2);
+    if (launches) ++*launches;
+  }
+  return 0;
+}
+
+}  // namespace tic

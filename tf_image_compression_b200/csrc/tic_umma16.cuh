@@ -28,8 +28,9 @@
 // accumulator (tests/probe/umma_accum_probe.cu), so the K steps rotate over nsplit accumulators that the
 // epilogue sums with round-to-nearest adds — and two tile buffers so the epilogue of tile i overlaps the
 // MMAs of tile i+1.
-// Warp roles (256 threads): 0 TMA producer, 1 MMA issuer (elect.sync: a plain `if (lane == 0)` region makes
-// ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop), 2 TMEM allocator, 4-7 epilogue.
+// Warp roles (384 threads): 0 TMA producer, 1 MMA issuer (elect.sync: a plain `if (lane == 0)` region makes
+// ptxas wrap every UTCHMMA in an ELECT / BRA.U.ANY loop), 2 TMEM allocator, 4-11 epilogue (two warps per TMEM
+// lane quadrant, alternating 16-column chunks).
 #pragma once
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -45,7 +46,7 @@ namespace tic {
 
 enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2 };
 
-constexpr int kU16Threads = 256;
+constexpr int kU16Threads = 384;
 constexpr int kU16MaxSlots = 6;
 
 struct U16Params {
@@ -157,6 +158,43 @@ __device__ __forceinline__ uint64_t u16_desc(uint32_t lo32, uint32_t hi32) {
   return d;
 }
 
+// Issue the MMAs of one plane of one K-block: 9 taps x ksteps.  Fully unrolled with compile-time tap
+// indices so the single issuing lane spends a handful of uniform-datapath instructions per MMA (the
+// tensor pipe needs >= 85 cycles per instruction; a rolled loop with div/mod cost 250).
+//   plane 0: A_hi x [W_hi ; W_lo'] (N = 2 npad) -> (D_main | D_lo);  plane 1: A_lo' x W_hi (N = npad) -> D_lo
+template <int MODE>
+__device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
+                                                uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
+                                                uint32_t tapw, int ksteps, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
+                                                bool fresh_kb) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const uint32_t ad = abase + (p.a_off[tap] >> 4);
+    const uint32_t bd = wbase + (uint32_t)tap * tapw;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks < ksteps) {
+        uint32_t d, accumulate;
+        if (MODE == U16_DECONV) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int kh = tap / 3, kw = tap - kh * 3;
+          const uint32_t ph = (uint32_t)((kh == 1) * 2 + (kw == 1));
+          d = dplane + ph * pairw;
+          const bool first_tap = (tap == 0 || tap == 1 || tap == 3 || tap == 4);
+          accumulate = (fresh_kb && first_tap && ks == 0) ? 0u : 1u;
+        } else {
+          d = dplane + sp * pairw;
+          sp = (sp + 1u) & smask;
+          accumulate = fresh_left ? 0u : 1u;
+          fresh_left = fresh_left ? fresh_left - 1u : 0u;
+        }
+        ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
+      }
+    }
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kU16Threads, 1)
 u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const U16Params p,
@@ -168,9 +206,11 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint8_t* s_a = smem + ((p.w_bytes + 1023u) & ~1023u);            // S plane slots
   U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_a + (size_t)p.S * p.slot_bytes);
   __shared__ unsigned s_hist[256];
+  __shared__ float s_bias[128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  if (tid < 128) s_bias[tid] = (tid < NPAD && p.oc0 + tid < a.cout) ? a.bias[p.oc0 + tid] : 0.f;
   if (tid == 0) {
     ptx::mbar_init(&bars->w_full, 1);
     for (int i = 0; i < p.S; ++i) {
@@ -179,7 +219,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
-      ptx::mbar_init(&bars->acc_empty[i], 4);
+      ptx::mbar_init(&bars->acc_empty[i], 8);
     }
     ptx::fence_barrier_init();
   }
@@ -240,7 +280,8 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const uint32_t idesc_lo = ptx::make_idesc_f16(128, NPAD);      // A_lo' x W_hi -> D_lo
     const uint32_t a_hi32 = (p.sbo >> 4) | (1u << 14) | (p.a_layout << 29);
     const uint32_t w_hi32 = (p.w_sbo >> 4) | (1u << 14) | (p.w_layout << 29);
-    const uint32_t tapw = p.tap_bytes >> 4;
+    const uint32_t tapw = p.tap_bytes >> 4, pairw = 2u * (uint32_t)NPAD, smask = (uint32_t)p.nsplit - 1u;
+    const int ksteps = p.ksteps;
     ptx::mbar_wait(&bars->w_full, 0);
     uint32_t it = 0, ti = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
@@ -257,35 +298,9 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           if (ptx::elect_one()) {
             const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
             const uint32_t wbase = (ptx::smem_u32(s_w + (size_t)kb * 9 * p.tap_bytes) >> 4) | (1u << 16);
-            const uint32_t idesc = plane ? idesc_lo : idesc_st;
-            const uint32_t dplane = dbase + (plane ? (uint32_t)NPAD : 0u);
-            uint32_t step = (uint32_t)kb * 9u * (uint32_t)p.ksteps;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t ad = abase + (p.a_off[tap] >> 4);
-              const uint32_t bd = wbase + (uint32_t)tap * tapw;
-              uint32_t acc, fresh;
-              if (MODE == U16_DECONV) {
-                const int kh = tap / 3, kw = tap - kh * 3;
-                acc = (uint32_t)((kh == 1) * 2 + (kw == 1));
-                fresh = (kb == 0 && plane == 0 && (tap == 0 || tap == 1 || tap == 3 || tap == 4)) ? 1u : 0u;
-              } else {
-                acc = 0;
-                fresh = 0;
-              }
-              for (int ks = 0; ks < p.ksteps; ++ks, ++step) {
-                uint32_t d, accumulate;
-                if (MODE == U16_DECONV) {
-                  d = dplane + acc * 2u * (uint32_t)NPAD;
-                  accumulate = (fresh && ks == 0) ? 0u : 1u;
-                } else {
-                  const uint32_t sp = step % (uint32_t)p.nsplit;
-                  d = dplane + sp * 2u * (uint32_t)NPAD;
-                  accumulate = (plane == 0 && step < (uint32_t)p.nsplit) ? 0u : 1u;
-                }
-                ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
-              }
-            }
+            uint32_t sp = 0, fresh_left = (plane == 0 && kb == 0) ? (uint32_t)p.nsplit : 0u;
+            u16_issue_plane<MODE>(p, abase, wbase, dbase + (plane ? (uint32_t)NPAD : 0u), pairw, plane ? idesc_lo : idesc_st,
+                                  a_hi32, w_hi32, tapw, ksteps, smask, sp, fresh_left, plane == 0 && kb == 0);
           }
           __syncwarp();
           if (ptx::elect_one()) ptx::tc_commit(&bars->empty[s]);
@@ -298,6 +313,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   } else if (warp >= 4) {
     // ===== epilogue: TMEM -> registers -> sum splits / bias / act / residual -> pair planes | f32 | symbols =====
     const int q4 = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;   // which 16-column chunks this warp takes
     const int m = q4 * 32 + lane;       // tile row = pixel
     const int grp = m >> 3, xx = m & 7;
     const int hh = grp / p.bn, nb = grp % p.bn;
@@ -320,7 +336,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       for (int ph = 0; ph < phases; ++ph) {
         const int y = MODE == U16_DECONV ? 2 * yt + (ph >> 1) : yt;
         const int x = MODE == U16_DECONV ? 2 * xt + (ph & 1) : xt;
-        for (int c = 0; c < NPAD; c += 16) {
+        for (int c = half * 16; c < NPAD; c += 32) {
           float v[16];
           if (MODE == U16_DECONV || p.nsplit == 1) {
             float u[16];
@@ -355,8 +371,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           if (valid && oc < a.cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float bb = (oc + i < a.cout) ? __ldg(a.bias + oc + i) : 0.f;
-              v[i] = apply_act(__fadd_rn(v[i], bb), a.act);
+              v[i] = apply_act(__fadd_rn(v[i], s_bias[cl + i]), a.act);
             }
             const long long pix = ((long long)n * a.hout + y) * a.wout + x;
             if (a.res) {
@@ -413,7 +428,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
     }
-    // symbol histogram (quantising layers): reduce the 4 epilogue warps through shared memory
+    // symbol histogram (quantising layers): reduce the epilogue warps through shared memory
     if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
       if (a.q == 2) {
         h_ones = __reduce_add_sync(0xffffffffu, h_ones);
@@ -423,8 +438,8 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           if (h_valid - h_ones) atomicAdd(&s_hist[0], (unsigned)(h_valid - h_ones));
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
-      for (int i = tid - 128; i < a.q; i += 128)
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the eight epilogue warps only
+      for (int i = tid - 128; i < a.q; i += 256)
         if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
     }
   }
@@ -549,12 +564,16 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   } else {
     if (pair > 512) return false;
     p.nbuf = pair * 2 <= 512 ? 2 : 1;
-    p.nsplit = std::max(1, std::min(4, (512 / p.nbuf) / pair));
-    p.nsplit = std::min(p.nsplit, std::max(1, p.KB * 9 * p.ksteps / 4));
+    // the tensor core truncates when adding into the accumulator: keep <= ~18 accumulation steps per
+    // accumulator (what a 32-channel layer has unsplit), power of two, as TMEM allows
+    const int steps = p.KB * 9 * p.ksteps;
+    const int cap = (512 / p.nbuf) / pair;
+    p.nsplit = 1;
+    while (p.nsplit * 2 <= cap && p.nsplit < 4 && steps > 18 * p.nsplit) p.nsplit *= 2;
     p.acc_cols = (uint32_t)(p.nsplit * pair);
   }
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
-  const size_t budget = 227 * 1024 - 1024 /* static histogram */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
+  const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
   const size_t wres = (p.w_bytes + 1023u) & ~1023u;
   if (wres + 2 * (size_t)p.slot_bytes > budget) return false;
   p.S = (int)std::min<size_t>(kU16MaxSlots, (budget - wres) / p.slot_bytes);

@@ -13,6 +13,7 @@
 #include "tic_simt.cuh"
 #include "tic_umma.cuh"
 #include "tic_umma16.cuh"
+#include "tic_first16.cuh"
 
 using namespace tic;
 
@@ -26,6 +27,7 @@ struct Layer {
   float* b = nullptr;     // device [cout]
   UmmaWeights uw;         // tensor-path operand images (built lazily from w)
   U16Weights uw16;        // fp16-pair operand images
+  F16Weights fw16;        // fp16-pair first-layer (cin = 3) operand image
   bool loaded = false;
 };
 
@@ -384,7 +386,11 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
       cudaEventCreate(&pr.e1);
       cudaEventRecord(pr.e0, h->stream);
     }
-    if (pair16 && u16_supported(a, d.kind, d.stride)) {
+    if (pair16 && f16_first_supported(a, d.kind, d.stride)) {
+      int nl = 0;
+      rc = launch_first16(h->stream, a, d.stride, ly.w, &ly.fw16, h->num_sms, &h->err, &nl);
+      h->launches += nl;
+    } else if (pair16 && u16_supported(a, d.kind, d.stride)) {
       int nl = 0;
       rc = launch_u16(h->stream, a, d.kind, d.stride, ly.w, &ly.uw16, h->num_sms, &h->err, &nl);
       h->launches += nl;
@@ -575,6 +581,7 @@ void tic_destroy(tic_codec* h) {
       if (l.b) cudaFree(l.b);
       l.uw.release();
       l.uw16.release();
+      l.fw16.release();
     }
     if (h->g[gi].d_normlut) cudaFree(h->g[gi].d_normlut);
   }
@@ -655,6 +662,7 @@ int tic_set_graph(tic_codec* h, int graph, const tic_layer_desc* layers, int n_l
     if (l.b) cudaFree(l.b);
     l.uw.release();
     l.uw16.release();
+      l.fw16.release();
   }
   g.layers.assign(n_layers, Layer());
   for (int i = 0; i < n_layers; ++i) {
@@ -689,6 +697,7 @@ int tic_load_weights(tic_codec* h, int graph, int layer, const float* kernel, co
   TIC_CUDA(h, cudaMemcpy(l.b, bias, (size_t)cout * sizeof(float), cudaMemcpyHostToDevice));
   l.uw.release();
   l.uw16.release();
+      l.fw16.release();
   l.loaded = true;
   return TIC_OK;
 }

@@ -1,0 +1,599 @@
+// First layer of the encoder / post-filter on the tensor pipe: 3x3 conv over 3 input channels (K = 27,
+// padded to 32), stride 1 or 2, with the reference's input pipeline fused into the operand build:
+//   utils.crop_image_input_patches (utils/utils.py:96-133: reflect pad, row-major patch grid)  -> index arithmetic
+//   (x - mean) / std                (model_0/model.py:44)                                       -> 3 x 256 table (u8) | true division (f32)
+//   basic_block.my_conv2d           (basic_block/basic_block.py:27-47)                          -> tcgen05.mma kind::f16, fp16 pairs
+// With 3 input channels there is nothing for TMA to tile (a pixel is 3 bytes), so four builder warps
+// write the im2col tile themselves: one thread per output pixel gathers its 27 normalised inputs, splits
+// them into (hi, lo') fp16 pairs and stores one 64-byte row per plane in the SWIZZLE_64B K-major layout the
+// MMA descriptors read.  Per 128-pixel tile: 2 K-steps x (A_hi x [W_hi ; W_lo'] + A_lo' x W_hi) = 4 MMAs.
+// Warp roles (544 threads): 0-7 builders (two groups of 128 threads on alternating tiles: the gather is
+// latency-bound, all 27 loads of a pixel are issued before any is used), 8-15 epilogue (shared with
+// tic_umma16.cuh), 16 MMA issuer + TMEM.
+#pragma once
+#include "tic_umma16.cuh"
+
+namespace tic {
+
+constexpr int kF16Threads = 544;
+constexpr int kF16Stages = 4;
+constexpr uint32_t kF16StageBytes = 16384;  // hi plane 128 x 64 B | lo' plane 128 x 64 B
+
+struct F16Params {
+  int n;                 // patches
+  int P;                 // input patch edge
+  int stride, pad;       // TF SAME: stride 2 on even maps pads (0, 1); stride 1 pads (1, 1)
+  int bn, bh;
+  int tiles_x, tiles_y;
+  long long num_tiles;
+  int npad;
+  int nbuf;              // TMEM tile buffers (power of two, <= 4)
+  const uint8_t* wimg;   // [W_hi npad rows ; W_lo' npad rows] x 64 B, SW64
+};
+
+struct F16SmemBars {
+  uint64_t full[kF16Stages], empty[kF16Stages];
+  uint64_t acc_full[4], acc_empty[4];
+  uint32_t tmem_base;
+};
+
+// device [9][3][cout] fp32 -> [hi rows npad | lo' rows npad][32] fp16, k = tap * 3 + c, swizzled 64-byte rows
+__global__ void f16_build_weights_kernel(const float* __restrict__ w, int cout, int npad, uint8_t* __restrict__ img) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npad * 32; i += gridDim.x * blockDim.x) {
+    const int k = i & 31, oc = i >> 5;
+    const float v = (k < 27 && oc < cout) ? w[k * cout + oc] : 0.f;
+    __half hi, lo;
+    split16(v, hi, lo);
+    *reinterpret_cast<__half*>(img + u16_swz((uint32_t)oc * 64u + k * 2, 64)) = hi;
+    *reinterpret_cast<__half*>(img + u16_swz((uint32_t)(npad + oc) * 64u + k * 2, 64)) = lo;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+template <int S>
+__global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Params p, const LayerArgs a) {
+  const int NPAD = p.npad;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;                                        // kF16Stages stages
+  uint8_t* s_w = smem + kF16Stages * kF16StageBytes;          // 2 * npad * 64 B
+  F16SmemBars* bars = reinterpret_cast<F16SmemBars*>(s_w + 2 * 64 * 64);
+  __shared__ unsigned s_hist[256];
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ float s_lut[3 * 256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < 128) s_bias[tid] = (tid < NPAD && tid < a.cout) ? a.bias[tid] : 0.f;
+  for (int i = tid; i < 256; i += kF16Threads) s_hist[i] = 0;
+  if (a.in_mode == IO_U8_NORM)
+    for (int i = tid; i < 3 * 256; i += kF16Threads) s_lut[i] = a.lut[i];
+  for (int i = tid; i < 2 * NPAD * 4; i += kF16Threads)  // weight image, 16-byte chunks
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  if (tid == 0) {
+    for (int i = 0; i < kF16Stages; ++i) {
+      ptx::mbar_init(&bars->full[i], 4);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&bars->acc_full[i], 1);
+      ptx::mbar_init(&bars->acc_empty[i], 8);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 16) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t pairw = 2u * (uint32_t)NPAD;
+  const uint32_t bmask = (uint32_t)p.nbuf - 1u;
+  int nbshift = 0;
+  while ((1 << nbshift) < p.nbuf) ++nbshift;
+
+  if (warp < 8) {
+    // ===== builders: one thread per tile row (output pixel); group g takes tiles it = g, g + 2, ... =====
+    const int group = warp >> 2;
+    const int m = tid & 127;
+    const int grp = m >> 3, xx = m & 7;
+    const int hh = grp / p.bn, nb = grp % p.bn;
+    const uint32_t sw = (uint32_t)((m >> 1) & 3);
+    const Geo g = a.geo;
+    const unsigned per_img = (unsigned)(g.gh * g.gw);
+    uint32_t it = (uint32_t)group;
+    for (long long tile = blockIdx.x + (long long)group * gridDim.x; tile < p.num_tiles; tile += 2LL * gridDim.x, it += 2) {
+      long long tt = tile;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
+      const int oy = ty * p.bh + hh, ox = tx * 8 + xx;
+      // patch -> image geometry (utils/utils.py:96-133); reflect only ever fires on padded image borders
+      const bool nok = n < p.n;
+      const unsigned gp = (unsigned)(g.n0 + (nok ? n : 0));
+      const unsigned img = gp / per_img;
+      const unsigned r = gp - img * per_img;
+      const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+      const int Y0 = g.oy + (int)gy * g.P, X0 = g.ox + (int)gx * g.P;
+      const long long img_off = (long long)img * g.H * g.W;
+      long long off[9];
+      bool ok[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int iy = oy * S + kh - p.pad;
+        const bool yok = nok && iy >= 0 && iy < p.P;
+        const long long row = img_off + (long long)reflect_index(Y0 + (yok ? iy : 0), g.H) * g.W;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ix = ox * S + kw - p.pad;
+          const bool xok = ix >= 0 && ix < p.P;
+          ok[kh * 3 + kw] = yok && xok;
+          off[kh * 3 + kw] = (row + reflect_index(X0 + (xok ? ix : 0), g.W)) * 3;
+        }
+      }
+      float v[27];
+      if (a.in_mode == IO_U8_NORM) {
+        // all 27 byte loads first (independent, always in bounds), then the table look-ups
+        unsigned b[27];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint8_t* q = reinterpret_cast<const uint8_t*>(a.in) + off[t];
+          b[3 * t] = q[0];
+          b[3 * t + 1] = q[1];
+          b[3 * t + 2] = q[2];
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          v[3 * t] = ok[t] ? s_lut[b[3 * t]] : 0.f;
+          v[3 * t + 1] = ok[t] ? s_lut[256 + b[3 * t + 1]] : 0.f;
+          v[3 * t + 2] = ok[t] ? s_lut[512 + b[3 * t + 2]] : 0.f;
+        }
+      } else {
+        float b[27];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const float* q = reinterpret_cast<const float*>(a.in) + off[t];
+          b[3 * t] = q[0];
+          b[3 * t + 1] = q[1];
+          b[3 * t + 2] = q[2];
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          v[3 * t] = ok[t] ? tic_normalize(b[3 * t], a.mean[0], a.stdv[0]) : 0.f;
+          v[3 * t + 1] = ok[t] ? tic_normalize(b[3 * t + 1], a.mean[1], a.stdv[1]) : 0.f;
+          v[3 * t + 2] = ok[t] ? tic_normalize(b[3 * t + 2], a.mean[2], a.stdv[2]) : 0.f;
+        }
+      }
+      uint32_t hp[16], lp[16];
+#pragma unroll
+      for (int k = 0; k < 32; k += 2) {
+        __half h0 = __float2half_rn(0.f), l0 = h0, h1 = h0, l1 = h0;
+        if (k < 27) split16(v[k], h0, l0);
+        if (k + 1 < 27) split16(v[k + 1], h1, l1);
+        hp[k >> 1] = pack_half2(h0, h1);
+        lp[k >> 1] = pack_half2(l0, l1);
+      }
+      const int s = it % kF16Stages;
+      ptx::mbar_wait(&bars->empty[s], ((it / kF16Stages) & 1) ^ 1);
+      uint8_t* rowh = s_a + (size_t)s * kF16StageBytes + (uint32_t)m * 64u;
+      uint8_t* rowl = rowh + 8192;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t c = ((uint32_t)j ^ sw) << 4;
+        *reinterpret_cast<uint4*>(rowh + c) = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+        *reinterpret_cast<uint4*>(rowl + c) = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
+    }
+  } else if (warp == 16) {
+    // ===== MMA issuer =====
+    const uint32_t idesc_st = ptx::make_idesc_f16(128, 2 * NPAD);
+    const uint32_t idesc_lo = ptx::make_idesc_f16(128, NPAD);
+    const uint32_t hi32 = (512u >> 4) | (1u << 14) | (4u << 29);  // SBO 512 B, SWIZZLE_64B
+    const uint32_t wbase = (ptx::smem_u32(s_w) >> 4) | (1u << 16);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int s = it % kF16Stages;
+      const uint32_t b = it & bmask;
+      ptx::mbar_wait(&bars->acc_empty[b], ((it >> nbshift) & 1) ^ 1);
+      ptx::mbar_wait(&bars->full[s], (it / kF16Stages) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * kF16StageBytes) >> 4) | (1u << 16);
+        const uint32_t al = ah + (8192u >> 4);
+        const uint32_t d = tmem_base + b * pairw;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          ptx::mma_f16_ss(d, u16_desc(ah + 2u * ks, hi32), u16_desc(wbase + 2u * ks, hi32), idesc_st, ks ? 1u : 0u);
+          ptx::mma_f16_ss(d + (uint32_t)NPAD, u16_desc(al + 2u * ks, hi32), u16_desc(wbase + 2u * ks, hi32), idesc_lo, 1u);
+        }
+      }
+      __syncwarp();
+      if (ptx::elect_one()) {
+        ptx::tc_commit(&bars->empty[s]);
+        ptx::tc_commit(&bars->acc_full[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue (warps 8-15) =====
+    const int q4 = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const int m = q4 * 32 + lane;
+    const int grp = m >> 3, xx = m & 7;
+    const int hh = grp / p.bn, nb = grp % p.bn;
+    int h_ones = 0, h_valid = 0;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & bmask;
+      ptx::mbar_wait(&bars->acc_full[b], (it >> nbshift) & 1);
+      ptx::tc_fence_after();
+      long long tt = tile;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
+      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
+      u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * p.bh + hh, tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
+                                h_valid);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
+    }
+    if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
+      if (a.q == 2) {
+        h_ones = __reduce_add_sync(0xffffffffu, h_ones);
+        h_valid = __reduce_add_sync(0xffffffffu, h_valid);
+        if (lane == 0) {
+          if (h_ones) atomicAdd(&s_hist[1], (unsigned)h_ones);
+          if (h_valid - h_ones) atomicAdd(&s_hist[0], (unsigned)(h_valid - h_ones));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = tid - 256; i < a.q; i += 256)
+        if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- stride 2: no im2col at all ---------------------------------------------------------------------
+// The builders write the normalised, split INPUT tile once per pixel as RGB0 quads (8 bytes per pixel and
+// plane, row pitch kW2Pitch).  With stride 2 consecutive output pixels start 16 bytes apart, which is
+// exactly the row pitch of an un-swizzled K-major core matrix, so the A operand of filter row kh is a
+// descriptor over the input tile itself: start = pixel (2 oy0 + kh, 2 ox0), LBO (next 8 K elements) = 16
+// bytes = the next two pixels, SBO (next 8 output pixels = next output row) = two input rows.  A K-step
+// reads 4 pixels x 4 channels; the weight tile is zero for the 4th pixel and the 4th channel.
+constexpr int kW2Cols = 18;                       // input pixels per staged row: 2 * 8 + 1 halo + 1 over-read
+constexpr uint32_t kW2Pitch = kW2Cols * 8;        // 144 bytes
+constexpr int kW2Rows = 33;                       // 2 * 16 + 1
+constexpr uint32_t kW2Plane = 4864;               // >= 33 * 144, multiple of 128
+constexpr uint32_t kW2Stage = 2 * kW2Plane + 512; // hi | lo', 1024-aligned below
+constexpr int kW2Stages = 4;
+constexpr int kW2Threads = 544;                   // warps 0-7 builders, 8-15 epilogue, 16 MMA + TMEM
+
+// device [9][3][cout] fp32 -> per kh: [k group (2)][row (2 npad: hi, lo')][8 halves], k = px * 4 + c
+__global__ void f16_build_weights_s2_kernel(const float* __restrict__ w, int cout, int npad, uint8_t* __restrict__ img) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * npad * 16; i += gridDim.x * blockDim.x) {
+    const int k = i & 15, oc = (i >> 4) % npad, kh = i / (16 * npad);
+    const int px = k >> 2, c = k & 3;
+    const float v = (px < 3 && c < 3 && oc < cout) ? w[((kh * 3 + px) * 3 + c) * cout + oc] : 0.f;
+    __half hi, lo;
+    split16(v, hi, lo);
+    uint8_t* base = img + (size_t)kh * (64u * npad) + (size_t)(k >> 3) * (32u * npad) + (k & 7) * 2;
+    *reinterpret_cast<__half*>(base + (size_t)oc * 16) = hi;
+    *reinterpret_cast<__half*>(base + (size_t)(npad + oc) * 16) = lo;
+  }
+}
+
+struct W2SmemBars {
+  uint64_t full[kW2Stages], empty[kW2Stages];
+  uint64_t acc_full[4], acc_empty[4];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Params p, const LayerArgs a) {
+  const int NPAD = p.npad;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;                                  // kW2Stages stages of kW2Stage bytes
+  uint8_t* s_w = smem + kW2Stages * 10240;              // 192 * npad bytes
+  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_w + 192 * 64);
+  __shared__ unsigned s_hist[256];
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ float s_lut[3 * 256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < 128) s_bias[tid] = (tid < NPAD && tid < a.cout) ? a.bias[tid] : 0.f;
+  for (int i = tid; i < 256; i += kW2Threads) s_hist[i] = 0;
+  if (a.in_mode == IO_U8_NORM)
+    for (int i = tid; i < 3 * 256; i += kW2Threads) s_lut[i] = a.lut[i];
+  for (int i = tid; i < 12 * NPAD; i += kW2Threads)  // weight image, 16-byte chunks
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  if (tid == 0) {
+    for (int i = 0; i < kW2Stages; ++i) {
+      ptx::mbar_init(&bars->full[i], 8);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&bars->acc_full[i], 1);
+      ptx::mbar_init(&bars->acc_empty[i], 8);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 16) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t pairw = 2u * (uint32_t)NPAD;
+  const uint32_t bmask = (uint32_t)p.nbuf - 1u;
+  int nbshift = 0;
+  while ((1 << nbshift) < p.nbuf) ++nbshift;
+
+  if (warp < 8) {
+    // ===== builders: 256 threads stage the 33 x 18 input pixels of a tile, one pixel per thread and pass.
+    // The gather is latency-bound, so the raw bytes of tile i+1 are requested before tile i is converted. =====
+    const Geo g = a.geo;
+    const unsigned per_img = (unsigned)(g.gh * g.gw);
+    const bool u8in = a.in_mode == IO_U8_NORM;
+    auto request = [&](long long tile, uint32_t (&raw)[9], bool (&ok)[3]) {
+      long long tt = tile;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n = (int)(tt / p.tiles_y);
+      const unsigned gp = (unsigned)(g.n0 + n);
+      const unsigned img = gp / per_img;
+      const unsigned r = gp - img * per_img;
+      const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+      const int iy0 = 2 * ty * 16, ix0 = 2 * tx * 8;
+      const int Y0 = g.oy + (int)gy * g.P + iy0, X0 = g.ox + (int)gx * g.P + ix0;
+      const long long img_off = (long long)img * g.H * g.W;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const int u = tid + ps * 256;
+        const int ry = u / kW2Cols, cx = u - ry * kW2Cols;
+        ok[ps] = u < kW2Rows * kW2Cols && iy0 + ry < p.P && ix0 + cx < p.P;
+        raw[3 * ps] = raw[3 * ps + 1] = raw[3 * ps + 2] = 0u;
+        if (ok[ps]) {
+          const long long off = (img_off + (long long)reflect_index(Y0 + ry, g.H) * g.W + reflect_index(X0 + cx, g.W)) * 3;
+          if (u8in) {
+            const uint8_t* q = reinterpret_cast<const uint8_t*>(a.in) + off;
+            raw[3 * ps] = q[0];
+            raw[3 * ps + 1] = q[1];
+            raw[3 * ps + 2] = q[2];
+          } else {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(a.in) + off;
+            raw[3 * ps] = q[0];
+            raw[3 * ps + 1] = q[1];
+            raw[3 * ps + 2] = q[2];
+          }
+        }
+      }
+    };
+    uint32_t raw[9];
+    bool ok[3];
+    if ((long long)blockIdx.x < p.num_tiles) request(blockIdx.x, raw, ok);
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      uint32_t raw_n[9];
+      bool ok_n[3];
+      const long long nxt = tile + gridDim.x;
+      if (nxt < p.num_tiles) request(nxt, raw_n, ok_n);
+      uint2 vh[3], vl[3];
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        float f0 = 0.f, f1 = 0.f, f2 = 0.f;
+        if (ok[ps]) {
+          if (u8in) {
+            f0 = s_lut[raw[3 * ps]];
+            f1 = s_lut[256 + raw[3 * ps + 1]];
+            f2 = s_lut[512 + raw[3 * ps + 2]];
+          } else {
+            f0 = tic_normalize(__uint_as_float(raw[3 * ps]), a.mean[0], a.stdv[0]);
+            f1 = tic_normalize(__uint_as_float(raw[3 * ps + 1]), a.mean[1], a.stdv[1]);
+            f2 = tic_normalize(__uint_as_float(raw[3 * ps + 2]), a.mean[2], a.stdv[2]);
+          }
+        }
+        __half h0, l0, h1, l1, h2, l2;
+        split16(f0, h0, l0);
+        split16(f1, h1, l1);
+        split16(f2, h2, l2);
+        vh[ps] = make_uint2(pack_half2(h0, h1), pack_half2(h2, __float2half_rn(0.f)));
+        vl[ps] = make_uint2(pack_half2(l0, l1), pack_half2(l2, __float2half_rn(0.f)));
+      }
+      const int s = it % kW2Stages;
+      ptx::mbar_wait(&bars->empty[s], ((it / kW2Stages) & 1) ^ 1);
+      uint8_t* st = s_a + (size_t)s * 10240;
+#pragma unroll
+      for (int ps = 0; ps < 3; ++ps) {
+        const int u = tid + ps * 256;
+        if (u < kW2Rows * kW2Cols) {
+          *reinterpret_cast<uint2*>(st + (uint32_t)u * 8u) = vh[ps];
+          *reinterpret_cast<uint2*>(st + kW2Plane + (uint32_t)u * 8u) = vl[ps];
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
+#pragma unroll
+      for (int i = 0; i < 9; ++i) raw[i] = raw_n[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) ok[i] = ok_n[i];
+    }
+  } else if (warp == 16) {
+    // ===== MMA issuer: per tile 3 filter rows x (A_hi x [W_hi ; W_lo'] , A_lo' x W_hi) =====
+    const uint32_t idesc_st = ptx::make_idesc_f16(128, 2 * NPAD);
+    const uint32_t idesc_lo = ptx::make_idesc_f16(128, NPAD);
+    // un-swizzled K-major: lo word = addr >> 4 | LBO >> 4 << 16 ; hi word = SBO >> 4 | version 1 << 14 | layout 0
+    const uint32_t a_hi32 = ((2u * kW2Pitch) >> 4) | (1u << 14);
+    const uint32_t w_hi32 = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo = (16u >> 4) << 16, w_lbo = ((32u * (uint32_t)NPAD) >> 4) << 16;
+    const uint32_t wbase = (ptx::smem_u32(s_w) >> 4) | w_lbo;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int s = it % kW2Stages;
+      const uint32_t b = it & bmask;
+      ptx::mbar_wait(&bars->acc_empty[b], ((it >> nbshift) & 1) ^ 1);
+      ptx::mbar_wait(&bars->full[s], (it / kW2Stages) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * 10240) >> 4) | a_lbo;
+        const uint32_t al = ah + (kW2Plane >> 4);
+        const uint32_t d = tmem_base + b * pairw;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t wd = wbase + (uint32_t)kh * ((64u * (uint32_t)NPAD) >> 4);
+          ptx::mma_f16_ss(d, u16_desc(ah + (uint32_t)kh * (kW2Pitch >> 4), a_hi32), u16_desc(wd, w_hi32), idesc_st, kh ? 1u : 0u);
+          ptx::mma_f16_ss(d + (uint32_t)NPAD, u16_desc(al + (uint32_t)kh * (kW2Pitch >> 4), a_hi32), u16_desc(wd, w_hi32), idesc_lo, 1u);
+        }
+      }
+      __syncwarp();
+      if (ptx::elect_one()) {
+        ptx::tc_commit(&bars->empty[s]);
+        ptx::tc_commit(&bars->acc_full[b]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue (warps 8-15) =====
+    const int q4 = warp & 3;
+    const int half = (warp - 8) >> 2;
+    const int m = q4 * 32 + lane;
+    const int hh = m >> 3, xx = m & 7;
+    int h_ones = 0, h_valid = 0;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & bmask;
+      ptx::mbar_wait(&bars->acc_full[b], (it >> nbshift) & 1);
+      ptx::tc_fence_after();
+      long long tt = tile;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n = (int)(tt / p.tiles_y);
+      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
+      u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * 16 + hh, tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
+    }
+    if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
+      if (a.q == 2) {
+        h_ones = __reduce_add_sync(0xffffffffu, h_ones);
+        h_valid = __reduce_add_sync(0xffffffffu, h_valid);
+        if (lane == 0) {
+          if (h_ones) atomicAdd(&s_hist[1], (unsigned)h_ones);
+          if (h_valid - h_ones) atomicAdd(&s_hist[0], (unsigned)(h_valid - h_ones));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = tid - 256; i < a.q; i += 256)
+        if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline bool f16_first_supported(const LayerArgs& a, int kind, int stride) {
+  if (kind != 0 || a.cin != 3) return false;
+  if (a.in_mode != IO_U8_NORM && a.in_mode != IO_F32_NORM) return false;
+  if (a.cout % 16 != 0 || a.cout > 64) return false;
+  if (a.hin != a.win) return false;
+  if (stride == 2 && (a.hin != 2 * a.hout || a.win != 2 * a.wout)) return false;
+  if (a.wout % 8 != 0 || !(a.hout == 8 || a.hout % 16 == 0)) return false;
+  if (a.out_mode == IO_DENORM_F32 || a.out_mode == IO_DENORM_U8) return false;
+  return true;
+}
+
+struct F16Weights {
+  uint8_t* img = nullptr;
+  bool windowed = false;
+  void release() {
+    if (img) cudaFree(img);
+    img = nullptr;
+  }
+};
+
+inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, const float* w_dev, F16Weights* fw, int num_sms,
+                          std::string* err, int* launches) {
+  auto fail = [&](const std::string& what, int code) {
+    if (err) *err = what;
+    return code;
+  };
+  F16Params p{};
+  p.n = a.n;
+  p.P = a.hin;
+  p.stride = stride;
+  p.pad = stride == 1 ? 1 : 0;
+  p.bn = a.hout == 8 ? 2 : 1;
+  p.bh = a.hout == 8 ? 8 : 16;
+  p.tiles_x = a.wout / 8;
+  p.tiles_y = a.hout / p.bh;
+  p.num_tiles = (long long)p.tiles_x * p.tiles_y * ((a.n + p.bn - 1) / p.bn);
+  p.npad = a.cout;
+  p.nbuf = std::min(4, 512 / (2 * p.npad));
+  const bool windowed = stride == 2 && p.bn == 1;  // operands straight from the staged input tile (no im2col)
+  if (!fw->img || fw->windowed != windowed) {
+    fw->release();
+    if (cudaMalloc(&fw->img, 192 * 64) != cudaSuccess) return fail("cudaMalloc for first-layer weight image failed", -4);
+    fw->windowed = windowed;
+    cudaMemsetAsync(fw->img, 0, 192 * 64, stream);
+    if (windowed)
+      f16_build_weights_s2_kernel<<<8, 256, 0, stream>>>(w_dev, a.cout, p.npad, fw->img);
+    else
+      f16_build_weights_kernel<<<8, 256, 0, stream>>>(w_dev, a.cout, p.npad, fw->img);
+    if (cudaGetLastError() != cudaSuccess) return fail("first-layer weight image kernel failed", -2);
+  }
+  p.wimg = fw->img;
+  const size_t smem = kF16Stages * kF16StageBytes + 2 * 64 * 64 + sizeof(F16SmemBars) + 1024;
+  const size_t smem_w2 = kW2Stages * 10240 + 192 * 64 + sizeof(W2SmemBars) + 1024;
+  const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(f16_first_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(f16_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(f16_first_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w2) != cudaSuccess)
+      return fail("cudaFuncSetAttribute(first-layer kernel) failed", -2);
+    configured = true;
+  }
+  if (windowed)
+    f16_first_s2_kernel<<<grid, kW2Threads, smem_w2, stream>>>(p, a);
+  else if (stride == 1)
+    f16_first_kernel<1><<<grid, kF16Threads, smem, stream>>>(p, a);
+  else
+    f16_first_kernel<2><<<grid, kF16Threads, smem, stream>>>(p, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("first-layer tensor launch failed: ") + cudaGetErrorString(e), -2);
+  if (launches) ++*launches;
+  return 0;
+}
+
+}  // namespace tic

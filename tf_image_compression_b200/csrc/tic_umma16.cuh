@@ -44,7 +44,11 @@
 
 namespace tic {
 
-enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2 };
+// U16_DECONV: one (D_main | D_lo) pair per output phase, one MMA pair per filter tap (9 per K step).
+// U16_DECONV_PH ("phase-stacked", cout <= 32): N = (phase, channel); the taps that read the same input pixel
+// ("view": a / a-1 x b / b-1) are stacked along N with zero rows for the phases a view does not reach:
+// 4 MMA pairs per K step instead of 9, and it is what makes the 3-channel last layer a tensor-core layer.
+enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2, U16_DECONV_PH = 3 };
 
 constexpr int kU16Threads = 384;
 constexpr int kU16MaxSlots = 6;
@@ -59,7 +63,8 @@ struct U16Params {
   int KB;                // K-blocks (input-channel chunks of kc)
   int kc;                // channels per K-block
   int ksteps;            // MMAs (K = 16) per tap per K-block
-  int npad;              // output channels of this launch rounded up to 16 (MMA N = npad or 2 * npad)
+  int npad;              // output channels of this launch rounded up to 16 (MMA N = npad or 2 * npad); PH: 4 * cpad rounded up
+  int cpad;              // PH: channels per phase column block (4 | 16 | 32)
   int oc0;               // first output channel of this launch (slice)
   int nsplit;            // conv: accumulator pairs the K steps rotate over; deconv: 1
   int nbuf;              // TMEM tile buffers (1 | 2)
@@ -125,6 +130,33 @@ __global__ void u16_build_weights_kernel(const float* __restrict__ w, int cin, i
   }
 }
 
+// phase-stacked transposed conv: [kb][view dy*2+dx][hi rows neff | lo' rows neff][kc], row = phase * cpad + oc
+__global__ void u16_build_weights_ph_kernel(const float* __restrict__ w, int cin, int cout, int oc0, int cs, int neff, int cpad,
+                                            int kc, int KB, uint8_t* __restrict__ img) {
+  const uint32_t wrow = (uint32_t)kc * 2u;
+  const uint32_t view_bytes = 2u * neff * wrow;
+  const long long total = (long long)KB * 4 * neff * kc;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % kc);
+    const int row = (int)((i / kc) % neff);
+    const int t = (int)(i / ((long long)kc * neff));
+    const int kb = t / 4, view = t % 4;
+    const int dy = view >> 1, dx = view & 1;
+    const int ph = row / cpad, oc = row % cpad;
+    const int py = ph >> 1, px = ph & 1;
+    const int kh = py ? (dy ? 1 : -1) : (dy ? 0 : 2);
+    const int kw = px ? (dx ? 1 : -1) : (dx ? 0 : 2);
+    const int ic = kb * kc + k;
+    float v = 0.f;
+    if (ph < 4 && kh >= 0 && kw >= 0 && oc < cs && ic < cin) v = w[((size_t)(kh * 3 + kw) * cin + ic) * cout + oc0 + oc];
+    __half hi, lo;
+    split16(v, hi, lo);
+    uint8_t* base = img + (size_t)t * view_bytes;
+    *reinterpret_cast<__half*>(base + u16_swz((uint32_t)row * wrow + k * 2, wrow)) = hi;
+    *reinterpret_cast<__half*>(base + u16_swz((uint32_t)(neff + row) * wrow + k * 2, wrow)) = lo;
+  }
+}
+
 // fp32 NHWC -> fp16 pair planes (caller-provided f32 activations: tic_run_layers)
 __global__ void u16_split_f32_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long long count) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
@@ -158,24 +190,241 @@ __device__ __forceinline__ uint64_t u16_desc(uint32_t lo32, uint32_t hi32) {
   return d;
 }
 
-// Issue the MMAs of one plane of one K-block: 9 taps x ksteps.  Fully unrolled with compile-time tap
-// indices so the single issuing lane spends a handful of uniform-datapath instructions per MMA (the
-// tensor pipe needs >= 85 cycles per instruction; a rolled loop with div/mod cost 250).
-//   plane 0: A_hi x [W_hi ; W_lo'] (N = 2 npad) -> (D_main | D_lo);  plane 1: A_lo' x W_hi (N = npad) -> D_lo
+// Epilogue of one tile for one epilogue warp: TMEM lane = tile row = pixel (n, yt, xt); the warp takes
+// every other 16-column chunk (`half`).  Sums the split accumulators (round-to-nearest), rescales the lo'
+// accumulator, adds bias, activation, residual, and stores pair planes | f32 | symbols (+ histogram).
+// 16 accumulator columns of one pixel: sum the split accumulators (round-to-nearest), rescale the lo' part
+template <int MODE>
+__device__ __forceinline__ void u16_load_chunk(float (&v)[16], const uint32_t tbuf, const int NPAD, const int nsplit,
+                                               const int ph, const int c, const int cpad) {
+  constexpr bool kDeconv = MODE == U16_DECONV || MODE == U16_DECONV_PH;
+  if (kDeconv || nsplit == 1) {
+    float u[16];
+    const uint32_t t0 = tbuf + (MODE == U16_DECONV_PH ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
+    ptx::tmem_ld16_nowait(t0 + NPAD, u);
+    ptx::tmem_ld16_nowait(t0, v);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(u[i], 1.0f / 2048.0f, v[i]);
+  } else {
+    // lo' accumulators first (small), then the main accumulators, round-to-nearest adds
+    float lo[16];
+    ptx::tmem_ld16_nowait(tbuf + NPAD + c, lo);
+    ptx::tmem_ld16_nowait(tbuf + c, v);
+    ptx::tmem_ld_wait();
+    for (int j = 1; j < nsplit; ++j) {
+      float u[16], w[16];
+      ptx::tmem_ld16_nowait(tbuf + (uint32_t)j * 2u * NPAD + NPAD + c, u);
+      ptx::tmem_ld16_nowait(tbuf + (uint32_t)j * 2u * NPAD + c, w);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        lo[i] = __fadd_rn(lo[i], u[i]);
+        v[i] = __fadd_rn(v[i], w[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(lo[i], 1.0f / 2048.0f, v[i]);
+  }
+}
+
+// two values -> packed (hi, hi) and (lo', lo') half2 words; same arithmetic as split16
+__device__ __forceinline__ void split16x2(float v0, float v1, uint32_t& hp, uint32_t& lp) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(__fmul_rn(__fsub_rn(v0, hf.x), 2048.0f), __fmul_rn(__fsub_rn(v1, hf.y), 2048.0f));
+  hp = *reinterpret_cast<const uint32_t*>(&h);
+  lp = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// Epilogue of one tile for one epilogue warp: TMEM lane = tile row = pixel (n, yt, xt); the warp takes
+// every other 16-column chunk (`half`).  Adds bias, activation, residual, and stores pair planes | f32 |
+// symbols (+ histogram) | the denormalised, clipped, rounded image (3-channel last layer).
+template <int MODE>
+__device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
+                                                  const uint32_t tbuf, const int n, const int yt, const int xt, const bool valid,
+                                                  const int half, const float* s_bias, unsigned* s_hist, int& h_ones,
+                                                  int& h_valid, const int cpad = 0) {
+  constexpr bool kDeconv = MODE == U16_DECONV || MODE == U16_DECONV_PH;
+  if (MODE == U16_DECONV_PH && cpad == 4) {
+    // 3-channel last layer: the 16 columns are (phase, channel) of the 2x2 output pixels of this input pixel;
+    // the two warps of a lane quadrant take the even / the odd output row
+    float v[16], u[16];
+    ptx::tmem_ld16_nowait(tbuf + NPAD, u);
+    ptx::tmem_ld16_nowait(tbuf, v);
+    ptx::tmem_ld_wait();
+    if (!valid) return;
+    if (a.out_mode == IO_DENORM_U8 || a.out_mode == IO_DENORM_F32) {
+      // patch -> image geometry once per pixel pair (utils.concat_patches, utils/utils.py:136-167: crop to [H, W])
+      const Geo& g = a.geo;
+      const unsigned per_img = (unsigned)(g.gh * g.gw);
+      const unsigned gp = (unsigned)(g.n0 + n);
+      const unsigned img = gp / per_img;
+      const unsigned r = gp - img * per_img;
+      const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+      const int Y = g.oy + (int)gy * g.P + 2 * yt + half, X = g.ox + (int)gx * g.P + 2 * xt;
+      if (Y >= g.H) return;
+      const long long off = (((long long)img * g.H + Y) * g.W + X) * 3;
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        if (X + px >= g.W) break;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int col = (half * 2 + px) * 4 + c;
+          // select with constant indices (v[] stays in registers): half is warp-uniform
+          const float m = half ? v[8 + px * 4 + c] : v[px * 4 + c];
+          const float l = half ? u[8 + px * 4 + c] : u[px * 4 + c];
+          (void)col;
+          float y = apply_act(__fadd_rn(__fmaf_rn(l, 1.0f / 2048.0f, m), s_bias[c]), a.act);
+          y = tic_denorm_clip(y, a.mean[c], a.stdv[c]);
+          if (a.out_mode == IO_DENORM_F32)
+            reinterpret_cast<float*>(a.out)[off + px * 3 + c] = y;
+          else
+            reinterpret_cast<uint8_t*>(a.out)[off + px * 3 + c] = (uint8_t)(int)rintf(y);
+        }
+      }
+      return;
+    }
+    if (half != 0) return;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = apply_act(__fadd_rn(__fmaf_rn(u[i], 1.0f / 2048.0f, v[i]), s_bias[i & 3]), a.act);
+#pragma unroll
+    for (int ph = 0; ph < 4; ++ph) store_pixel<4>(a, n, 2 * yt + (ph >> 1), 2 * xt + (ph & 1), oc0, v + 4 * ph, s_hist, h_ones, h_valid);
+    return;
+  }
+  const int phases = kDeconv ? 4 : 1;
+  const int cend = MODE == U16_DECONV_PH ? cpad : NPAD;
+  if (a.out_mode == IO_ACT16 && (a.cout & 15) == 0) {
+    // ---- fast path: pair-plane output, every chunk holds 16 real channels --------------------------------
+    const float floor_v = a.act ? 0.0f : -INFINITY;
+    const long long pix0 = ((long long)n * a.hout + (kDeconv ? 2 * yt : yt)) * a.wout + (kDeconv ? 2 * xt : xt);
+    __half* const obase = reinterpret_cast<__half*>(a.out) + pix0 * a.cout + oc0;
+    const __half* const rbase = a.res ? reinterpret_cast<const __half*>(a.res) + pix0 * a.cout + oc0 : nullptr;
+    for (int ph = 0; ph < phases; ++ph) {
+      const int poff = kDeconv ? ((ph >> 1) * a.wout + (ph & 1)) * a.cout : 0;
+      for (int c = half * 16; c < cend; c += 32) {
+        float v[16];
+        u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
+        if (!valid || oc0 + c >= a.cout) continue;
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = bp[i];
+          v[4 * i] = fmaxf(__fadd_rn(v[4 * i], b.x), floor_v);
+          v[4 * i + 1] = fmaxf(__fadd_rn(v[4 * i + 1], b.y), floor_v);
+          v[4 * i + 2] = fmaxf(__fadd_rn(v[4 * i + 2], b.z), floor_v);
+          v[4 * i + 3] = fmaxf(__fadd_rn(v[4 * i + 3], b.w), floor_v);
+        }
+        if (rbase) {
+          const uint4* rh = reinterpret_cast<const uint4*>(rbase + poff + c);
+          const uint4* rl = reinterpret_cast<const uint4*>(rbase + a.res_lo_off + poff + c);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 qh = __ldg(rh + j), ql = __ldg(rl + j);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+              v[8 * j + 2 * e] = __fadd_rn(__fmaf_rn(lf.x, 1.0f / 2048.0f, hf.x), v[8 * j + 2 * e]);
+              v[8 * j + 2 * e + 1] = __fadd_rn(__fmaf_rn(lf.y, 1.0f / 2048.0f, hf.y), v[8 * j + 2 * e + 1]);
+            }
+          }
+        }
+        uint32_t hp[8], lp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
+        uint4* oh = reinterpret_cast<uint4*>(obase + poff + c);
+        uint4* ol = reinterpret_cast<uint4*>(obase + a.out_lo_off + poff + c);
+        oh[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        oh[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+        ol[0] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        ol[1] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+      }
+    }
+    return;
+  }
+  for (int ph = 0; ph < phases; ++ph) {
+    const int y = kDeconv ? 2 * yt + (ph >> 1) : yt;
+    const int x = kDeconv ? 2 * xt + (ph & 1) : xt;
+    for (int c = half * 16; c < cend; c += 32) {
+      float v[16];
+      u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
+      const int cl = c;          // channel inside the slice
+      const int oc = oc0 + cl;   // channel of the layer
+      if (valid && oc < a.cout) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(__fadd_rn(v[i], s_bias[cl + i]), a.act);
+        const long long pix = ((long long)n * a.hout + y) * a.wout + x;
+        if (a.res) {
+          if (a.res16) {
+            const __half* rh = reinterpret_cast<const __half*>(a.res) + pix * a.cout + oc;
+            const __half* rl = rh + a.res_lo_off;
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              if (oc + i < a.cout) {
+                const uint4 qh = __ldg(reinterpret_cast<const uint4*>(rh + i));
+                const uint4 ql = __ldg(reinterpret_cast<const uint4*>(rl + i));
+                const __half* ph8 = reinterpret_cast<const __half*>(&qh);
+                const __half* pl8 = reinterpret_cast<const __half*>(&ql);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[i + e] = __fadd_rn(join16(ph8[e], pl8[e]), v[i + e]);
+              }
+            }
+          } else {
+            const float* rp = a.res + pix * a.cout + oc;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (oc + i < a.cout) {
+                const float4 r = __ldg(reinterpret_cast<const float4*>(rp + i));
+                v[i] = __fadd_rn(r.x, v[i]);
+                v[i + 1] = __fadd_rn(r.y, v[i + 1]);
+                v[i + 2] = __fadd_rn(r.z, v[i + 2]);
+                v[i + 3] = __fadd_rn(r.w, v[i + 3]);
+              }
+            }
+          }
+        }
+        if (a.out_mode == IO_ACT16) {
+          __half* oh = reinterpret_cast<__half*>(a.out) + pix * a.cout + oc;
+          __half* ol = oh + a.out_lo_off;
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            if (oc + i < a.cout) {
+              uint4 qh, ql;
+              __half* ph8 = reinterpret_cast<__half*>(&qh);
+              __half* pl8 = reinterpret_cast<__half*>(&ql);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) split16(v[i + e], ph8[e], pl8[e]);
+              *reinterpret_cast<uint4*>(oh + i) = qh;
+              *reinterpret_cast<uint4*>(ol + i) = ql;
+            }
+          }
+        } else {
+          store_pixel<16>(a, n, y, x, oc, v, s_hist, h_ones, h_valid);
+        }
+      }
+    }
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
                                                 uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
                                                 uint32_t tapw, int ksteps, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
                                                 bool fresh_kb) {
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
+  for (int tap = 0; tap < (MODE == U16_DECONV_PH ? 4 : 9); ++tap) {  // PH: tap = view
     const uint32_t ad = abase + (p.a_off[tap] >> 4);
     const uint32_t bd = wbase + (uint32_t)tap * tapw;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       if (ks < ksteps) {
         uint32_t d, accumulate;
-        if (MODE == U16_DECONV) {
+        if (MODE == U16_DECONV_PH) {
+          d = dplane;
+          accumulate = (fresh_kb && tap == 0 && ks == 0) ? 0u : 1u;
+        } else if (MODE == U16_DECONV) {
           constexpr int dummy = 0;
           (void)dummy;
           const int kh = tap / 3, kw = tap - kh * 3;
@@ -206,7 +455,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint8_t* s_a = smem + ((p.w_bytes + 1023u) & ~1023u);            // S plane slots
   U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_a + (size_t)p.S * p.slot_bytes);
   __shared__ unsigned s_hist[256];
-  __shared__ float s_bias[128];
+  __shared__ __align__(16) float s_bias[128];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -297,7 +546,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
-            const uint32_t wbase = (ptx::smem_u32(s_w + (size_t)kb * 9 * p.tap_bytes) >> 4) | (1u << 16);
+            const uint32_t wbase = (ptx::smem_u32(s_w + (size_t)kb * (MODE == U16_DECONV_PH ? 4 : 9) * p.tap_bytes) >> 4) | (1u << 16);
             uint32_t sp = 0, fresh_left = (plane == 0 && kb == 0) ? (uint32_t)p.nsplit : 0u;
             u16_issue_plane<MODE>(p, abase, wbase, dbase + (plane ? (uint32_t)NPAD : 0u), pairw, plane ? idesc_lo : idesc_st,
                                   a_hi32, w_hi32, tapw, ksteps, smask, sp, fresh_left, plane == 0 && kb == 0);
@@ -317,7 +566,6 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const int m = q4 * 32 + lane;       // tile row = pixel
     const int grp = m >> 3, xx = m & 7;
     const int hh = grp / p.bn, nb = grp % p.bn;
-    const int phases = MODE == U16_DECONV ? 4 : 1;
     int h_ones = 0, h_valid = 0;
     uint32_t ti = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
@@ -333,97 +581,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
-      for (int ph = 0; ph < phases; ++ph) {
-        const int y = MODE == U16_DECONV ? 2 * yt + (ph >> 1) : yt;
-        const int x = MODE == U16_DECONV ? 2 * xt + (ph & 1) : xt;
-        for (int c = half * 16; c < NPAD; c += 32) {
-          float v[16];
-          if (MODE == U16_DECONV || p.nsplit == 1) {
-            float u[16];
-            const uint32_t t0 = tbuf + (uint32_t)ph * 2u * NPAD + c;
-            ptx::tmem_ld16_nowait(t0 + NPAD, u);
-            ptx::tmem_ld16_nowait(t0, v);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(u[i], 1.0f / 2048.0f, v[i]);
-          } else {
-            // lo' accumulators first (small), then the main accumulators, round-to-nearest adds
-            float lo[16];
-            ptx::tmem_ld16_nowait(tbuf + NPAD + c, lo);
-            ptx::tmem_ld16_nowait(tbuf + c, v);
-            ptx::tmem_ld_wait();
-            for (int j = 1; j < p.nsplit; ++j) {
-              float u[16], w[16];
-              ptx::tmem_ld16_nowait(tbuf + (uint32_t)j * 2u * NPAD + NPAD + c, u);
-              ptx::tmem_ld16_nowait(tbuf + (uint32_t)j * 2u * NPAD + c, w);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                lo[i] = __fadd_rn(lo[i], u[i]);
-                v[i] = __fadd_rn(v[i], w[i]);
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __fmaf_rn(lo[i], 1.0f / 2048.0f, v[i]);
-          }
-          const int cl = c;            // channel inside the slice
-          const int oc = p.oc0 + cl;   // channel of the layer
-          if (valid && oc < a.cout) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[i] = apply_act(__fadd_rn(v[i], s_bias[cl + i]), a.act);
-            }
-            const long long pix = ((long long)n * a.hout + y) * a.wout + x;
-            if (a.res) {
-              if (a.res16) {
-                const __half* rh = reinterpret_cast<const __half*>(a.res) + pix * a.cout + oc;
-                const __half* rl = rh + a.res_lo_off;
-#pragma unroll
-                for (int i = 0; i < 16; i += 8) {
-                  if (oc + i < a.cout) {
-                    const uint4 qh = __ldg(reinterpret_cast<const uint4*>(rh + i));
-                    const uint4 ql = __ldg(reinterpret_cast<const uint4*>(rl + i));
-                    const __half* ph8 = reinterpret_cast<const __half*>(&qh);
-                    const __half* pl8 = reinterpret_cast<const __half*>(&ql);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[i + e] = __fadd_rn(join16(ph8[e], pl8[e]), v[i + e]);
-                  }
-                }
-              } else {
-                const float* rp = a.res + pix * a.cout + oc;
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  if (oc + i < a.cout) {
-                    const float4 r = __ldg(reinterpret_cast<const float4*>(rp + i));
-                    v[i] = __fadd_rn(r.x, v[i]);
-                    v[i + 1] = __fadd_rn(r.y, v[i + 1]);
-                    v[i + 2] = __fadd_rn(r.z, v[i + 2]);
-                    v[i + 3] = __fadd_rn(r.w, v[i + 3]);
-                  }
-                }
-              }
-            }
-            if (a.out_mode == IO_ACT16) {
-              __half* oh = reinterpret_cast<__half*>(a.out) + pix * a.cout + oc;
-              __half* ol = oh + a.out_lo_off;
-#pragma unroll
-              for (int i = 0; i < 16; i += 8) {
-                if (oc + i < a.cout) {
-                  uint4 qh, ql;
-                  __half* ph8 = reinterpret_cast<__half*>(&qh);
-                  __half* pl8 = reinterpret_cast<__half*>(&ql);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) split16(v[i + e], ph8[e], pl8[e]);
-                  *reinterpret_cast<uint4*>(oh + i) = qh;
-                  *reinterpret_cast<uint4*>(ol + i) = ql;
-                }
-              }
-            } else {
-              store_pixel<16>(a, n, y, x, oc, v, s_hist, h_ones, h_valid);
-            }
-          }
-        }
-      }
+      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
@@ -459,15 +617,17 @@ inline int u16_mode_of(int kind, int stride) { return kind == 1 ? U16_DECONV : (
 inline bool u16_supported(const LayerArgs& a, int kind, int stride) {
   if (a.in_mode != IO_ACT16) return false;
   if (!(a.cin == 16 || a.cin == 32 || (a.cin % 64 == 0 && a.cin <= 512))) return false;
-  if (a.cout < 16) return false;  // 3-channel output layers: CUDA-core kernel
   const int mode = u16_mode_of(kind, stride);
+  const bool last3 = mode == U16_DECONV && a.cout <= 4;  // 3-channel last layer: phase-stacked deconv, N = 16
+  if (a.cout < 16 && !last3) return false;
+  if (last3 && a.out_mode == IO_ACT16) return false;
   const int Ht = mode == U16_DECONV ? a.hin : a.hout, Wt = mode == U16_DECONV ? a.win : a.wout;
   if (Wt % 8 != 0) return false;
   if (!(Ht == 8 || Ht % 16 == 0)) return false;
   if (mode == U16_S2 && (a.hin != 2 * a.hout || a.win != 2 * a.wout)) return false;
   if ((a.out_mode == IO_ACT16 || a.res16) && (a.cout % 8) != 0) return false;
   if ((a.out_mode == IO_ACT || (a.res && !a.res16)) && (a.cout % 4) != 0) return false;
-  if (a.out_mode == IO_DENORM_F32 || a.out_mode == IO_DENORM_U8) return false;
+  if ((a.out_mode == IO_DENORM_F32 || a.out_mode == IO_DENORM_U8) && !last3) return false;
   return true;
 }
 
@@ -507,6 +667,11 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   p.KB = a.cin / p.kc;
   p.ksteps = p.kc / 16;
   p.npad = (cs + 15) / 16 * 16;
+  if (p.mode == U16_DECONV && cs <= 32) {
+    p.mode = U16_DECONV_PH;
+    p.cpad = cs <= 4 ? 4 : (cs + 15) / 16 * 16;
+    p.npad = (4 * p.cpad + 15) / 16 * 16;  // N = (phase, channel)
+  }
   const uint32_t wrow = (uint32_t)p.kc * 2u;
   uint32_t arow = wrow;
   int box_rows, bw;
@@ -515,6 +680,13 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
     box_rows = bw * p.bn * (p.bh + 2);
     for (int kh = 0; kh < 3; ++kh)
       for (int kw = 0; kw < 3; ++kw) p.a_off[kh * 3 + kw] = (uint32_t)((kh * p.bn) * bw + kw) * arow;
+    p.sbo = (uint32_t)bw * arow;
+    p.nbox = 1;
+  } else if (p.mode == U16_DECONV_PH) {
+    bw = 9;
+    box_rows = bw * p.bn * (p.bh + 1);
+    // view (dy, dx) reads input row a - 1 + dy, column b - 1 + dx; box row 0 / column 0 = a-1 / b-1
+    for (int v = 0; v < 4; ++v) p.a_off[v] = (uint32_t)(((v >> 1) * p.bn) * bw + (v & 1)) * arow;
     p.sbo = (uint32_t)bw * arow;
     p.nbox = 1;
   } else if (p.mode == U16_DECONV) {
@@ -553,10 +725,14 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
     for (int kh = 0; kh < 3; ++kh) p.a_off[kh * 3 + 1] += p.box_stride;
   p.slot_bytes = p.box_stride * (uint32_t)p.nbox;
   p.tap_bytes = 2u * (uint32_t)p.npad * wrow;
-  p.w_bytes = (uint32_t)p.KB * 9u * p.tap_bytes;
+  p.w_bytes = (uint32_t)p.KB * (p.mode == U16_DECONV_PH ? 4u : 9u) * p.tap_bytes;
   // TMEM: conv nsplit pairs x 2 buffers; deconv 4 phase pairs
   const int pair = 2 * p.npad;
-  if (p.mode == U16_DECONV) {
+  if (p.mode == U16_DECONV_PH) {
+    p.nsplit = 1;
+    p.acc_cols = (uint32_t)pair;
+    p.nbuf = 2;
+  } else if (p.mode == U16_DECONV) {
     p.nsplit = 1;
     p.acc_cols = 4u * pair;
     if (p.acc_cols > 512) return false;
@@ -645,7 +821,10 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
       ws->mode = p.mode;
       ws->npad = p.npad;
       ws->oc0 = oc0;
-      u16_build_weights_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.kc, p.KB, ws->img);
+      if (p.mode == U16_DECONV_PH)
+        u16_build_weights_ph_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.cpad, p.kc, p.KB, ws->img);
+      else
+        u16_build_weights_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.kc, p.KB, ws->img);
       if (cudaGetLastError() != cudaSuccess) return fail("weight image kernel failed", -2);
     }
     p.wimg = ws->img;
@@ -655,6 +834,8 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
       e = u16_launch_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
     else if (p.mode == U16_S2)
       e = u16_launch_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    else if (p.mode == U16_DECONV_PH)
+      e = u16_launch_t<U16_DECONV_PH>(stream, tm[0], tm[1], p, a, grid, pl.smem);
     else
       e = u16_launch_t<U16_DECONV>(stream, tm[0], tm[1], p, a, grid, pl.smem);
     if (e != cudaSuccess) return fail(std::string("fp16-pair tensor launch failed: ") + cudaGetErrorString(e), -2);

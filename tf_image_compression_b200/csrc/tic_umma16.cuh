@@ -82,13 +82,16 @@ struct U16Params {
   uint32_t tap_bytes;    // [W_hi ; W_lo'] of one tap of one K-block
   uint32_t w_bytes;      // KB * 9 * tap_bytes
   const uint8_t* wimg;
+  int pair;              // 1: CTA-pair kernel (cta_group::2, M = 256)
+  uint32_t wA_bytes;     // pair: per-CTA bytes of its half of the stacked weight tiles (all taps, K-blocks)
+  uint32_t wB_bytes;     // pair: per-CTA bytes of its half of W_hi for the A_lo' x W_hi product
   long long in_lo_off;   // elements between the hi and lo' planes of the input (unused by the kernel: second tensor map)
 };
 
 struct U16WeightSlice {
   uint8_t* img = nullptr;
   size_t bytes = 0;
-  int mode = -1, npad = 0, oc0 = -1;
+  int mode = -1, npad = 0, oc0 = -1, pair = -1;
   void release() {
     if (img) cudaFree(img);
     img = nullptr;
@@ -154,6 +157,53 @@ __global__ void u16_build_weights_ph_kernel(const float* __restrict__ w, int cin
     uint8_t* base = img + (size_t)t * view_bytes;
     *reinterpret_cast<__half*>(base + u16_swz((uint32_t)row * wrow + k * 2, wrow)) = hi;
     *reinterpret_cast<__half*>(base + u16_swz((uint32_t)(neff + row) * wrow + k * 2, wrow)) = lo;
+  }
+}
+
+// CTA-pair weight image = the exact per-CTA shared-memory layout, per rank r of the pair:
+//   region A [kb][tap][rows nn]   : r = 0 -> W_hi rows, r = 1 -> W_lo' rows      (stacked product, N = 2 nn over the pair)
+//   region B [kb][tap][rows nn/2] : W_hi rows r * nn/2 ...                         (A_lo' x W_hi product, N = nn over the pair)
+// nn = npad (conv / tap-based deconv) or neff (phase-stacked deconv, row = phase * cpad + oc, tap = view).
+__global__ void u16_build_weights_pair_kernel(const float* __restrict__ w, int cin, int cout, int oc0, int cs, int nn, int cpad,
+                                              int ph_mode, int kc, int KB, uint32_t regA, uint32_t regB, uint8_t* __restrict__ img) {
+  const int T = ph_mode ? 4 : 9;
+  const uint32_t wrow = (uint32_t)kc * 2u;
+  const long long perA = (long long)KB * T * nn * kc, perB = perA / 2;
+  const long long total = 2 * (perA + perB);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int rank = (int)(i / (perA + perB));
+    long long j = i - (long long)rank * (perA + perB);
+    const bool inB = j >= perA;
+    if (inB) j -= perA;
+    const int rows = inB ? nn / 2 : nn;
+    const int k = (int)(j % kc);
+    const int rr = (int)((j / kc) % rows);
+    const int t = (int)(j / ((long long)kc * rows));
+    const int kb = t / T, tap = t % T;
+    const int row = inB ? rank * (nn / 2) + rr : rr;  // logical output row (channel or (phase, channel))
+    const bool want_lo = !inB && rank == 1;
+    int kh, kw, oc;
+    bool live = true;
+    if (ph_mode) {
+      const int dy = tap >> 1, dx = tap & 1, ph = row / cpad;
+      oc = row % cpad;
+      const int py = ph >> 1, px = ph & 1;
+      kh = py ? (dy ? 1 : -1) : (dy ? 0 : 2);
+      kw = px ? (dx ? 1 : -1) : (dx ? 0 : 2);
+      live = ph < 4 && kh >= 0 && kw >= 0;
+    } else {
+      kh = tap / 3;
+      kw = tap % 3;
+      oc = row;
+    }
+    const int ic = kb * kc + k;
+    float v = 0.f;
+    if (live && oc < cs && ic < cin) v = w[((size_t)(kh * 3 + kw) * cin + ic) * cout + oc0 + oc];
+    __half hi, lo;
+    split16(v, hi, lo);
+    const uint32_t off = (uint32_t)t * (uint32_t)rows * wrow + (uint32_t)rr * wrow + (uint32_t)k * 2u;
+    uint8_t* base = img + (size_t)rank * (regA + regB) + (inB ? regA : 0u);
+    *reinterpret_cast<__half*>(base + u16_swz(off, wrow)) = want_lo ? lo : hi;
   }
 }
 
@@ -408,7 +458,7 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
   }
 }
 
-template <int MODE>
+template <int MODE, bool PAIR = false>
 __device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
                                                 uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
                                                 uint32_t tapw, int ksteps, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
@@ -438,7 +488,10 @@ __device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t aba
           accumulate = fresh_left ? 0u : 1u;
           fresh_left = fresh_left ? fresh_left - 1u : 0u;
         }
-        ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
+        if (PAIR)
+          ptx::mma2_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
+        else
+          ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
       }
     }
   }
@@ -610,6 +663,197 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   }
 }
 
+// ---- CTA-pair variant (cta_group::2) ------------------------------------------------------------------
+// Measured (tests/probe/umma_2cta_probe.cu): an M = 256 MMA over a CTA pair costs 58 / 60 / 64 / 128 cycles
+// for N = 32 / 64 / 128 / 256 — less than the single-CTA M = 128 instruction (89 / 97 / 113 / 171) for twice
+// the rows.  Two CTAs of a cluster each own one 128-pixel tile: own TMA loads into own shared memory, own
+// TMEM, own epilogue; the leader's elected lane issues every MMA for both.  Each CTA keeps HALF of every
+// weight tile (leader W_hi, peer W_lo' for the stacked product; a half of W_hi each for A_lo' x W_hi).
+// Barriers: `full` lives in the leader and counts the bytes of both CTAs' boxes; `empty` and `acc_full` are
+// committed to both CTAs (multicast); `acc_empty` lives in the leader and collects both epilogues.
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kU16Threads, 1)
+u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const U16Params p,
+                const LayerArgs a) {
+  const int NPAD = p.npad;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_wA = smem;                                            // this CTA's half of the stacked weight tiles
+  uint8_t* s_wB = smem + ((p.wA_bytes + 1023u) & ~1023u);          // this CTA's half of W_hi
+  uint8_t* s_a = s_wB + ((p.wB_bytes + 1023u) & ~1023u);           // S plane slots
+  U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_a + (size_t)p.S * p.slot_bytes);
+  __shared__ unsigned s_hist[256];
+  __shared__ __align__(16) float s_bias[128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid < 128) s_bias[tid] = (tid < NPAD && p.oc0 + tid < a.cout) ? a.bias[p.oc0 + tid] : 0.f;
+  if (tid == 0) {
+    ptx::mbar_init(&bars->w_full, leader ? 2 : 1);  // leader: own bytes + the peer's "my weights landed"
+    for (int i = 0; i < p.S; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->acc_full[i], 1);
+      ptx::mbar_init(&bars->acc_empty[i], 16);        // 8 epilogue warps of each CTA (leader's copy is the live one)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc2(&bars->tmem_base, 512);
+    ptx::tmem_relinquish2();
+  }
+  for (int i = tid; i < 256; i += kU16Threads) s_hist[i] = 0;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // the peer's barriers exist before anything remote touches them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const long long npairs = gridDim.x >> 1, pair0 = blockIdx.x >> 1;
+  const long long num_pairs = (p.num_tiles + 1) >> 1;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own weight halves once, then per tile and K-block the two planes =====
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tm_hi);
+      ptx::prefetch_tmap(&tm_lo);
+      const uint8_t* src = p.wimg + (size_t)rank * (((p.wA_bytes + 1023u) & ~1023u) + ((p.wB_bytes + 1023u) & ~1023u));
+      ptx::mbar_expect_tx(&bars->w_full, p.wA_bytes + p.wB_bytes);
+      for (uint32_t off = 0; off < p.wA_bytes; off += 16384u)
+        ptx::bulk_load(s_wA + off, src + off, min(16384u, p.wA_bytes - off), &bars->w_full);
+      const uint8_t* srcB = src + ((p.wA_bytes + 1023u) & ~1023u);
+      for (uint32_t off = 0; off < p.wB_bytes; off += 16384u)
+        ptx::bulk_load(s_wB + off, srcB + off, min(16384u, p.wB_bytes - off), &bars->w_full);
+    }
+    __syncwarp();
+    if (!leader) {
+      ptx::mbar_wait(&bars->w_full, 0);
+      if (ptx::elect_one()) ptx::mbar_arrive_leader(&bars->w_full);
+      __syncwarp();
+    }
+    uint32_t it = 0;
+    for (long long tp = pair0; tp < num_pairs; tp += npairs) {
+      long long tt = 2 * tp + rank;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n0 = (int)(tt / p.tiles_y) * p.bn;
+      const int x0 = tx * 8, y0 = ty * p.bh;
+      for (int kb = 0; kb < p.KB; ++kb) {
+        for (int plane = 0; plane < 2; ++plane, ++it) {
+          const int s = it % p.S;
+          ptx::mbar_wait(&bars->empty[s], ((it / p.S) & 1) ^ 1);
+          if (ptx::elect_one()) {
+            const CUtensorMap* tm = plane ? &tm_lo : &tm_hi;
+            uint8_t* dst = s_a + (size_t)s * p.slot_bytes;
+            if (leader) ptx::mbar_expect_tx(&bars->full[s], 2u * p.box_bytes * (uint32_t)p.nbox);
+            if (MODE == U16_S2) {
+              ptx::tma2_load_5d(dst, tm, &bars->full[s], kb * p.kc, x0, 0, n0, y0);
+              if (p.nbox == 2) ptx::tma2_load_5d(dst + p.box_stride, tm, &bars->full[s], a.cin + kb * p.kc, x0, 0, n0, y0);
+            } else {
+              ptx::tma2_load_4d(dst, tm, &bars->full[s], kb * p.kc, x0 - 1, n0, y0 - 1);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (leader) {
+      const uint32_t idesc_st = ptx::make_idesc_f16(256, 2 * NPAD);
+      const uint32_t idesc_lo = ptx::make_idesc_f16(256, NPAD);
+      const uint32_t a_hi32 = (p.sbo >> 4) | (1u << 14) | (p.a_layout << 29);
+      const uint32_t w_hi32 = (p.w_sbo >> 4) | (1u << 14) | (p.w_layout << 29);
+      constexpr uint32_t T = MODE == U16_DECONV_PH ? 4u : 9u;
+      const uint32_t tapA = (uint32_t)NPAD * (uint32_t)p.kc * 2u, tapB = tapA >> 1;
+      const uint32_t pairw = 2u * (uint32_t)NPAD, smask = (uint32_t)p.nsplit - 1u;
+      const int ksteps = p.ksteps;
+      ptx::mbar_wait(&bars->w_full, 0);
+      uint32_t it = 0, ti = 0;
+      for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
+        const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
+        const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+        ptx::mbar_wait(&bars->acc_empty[b], (use & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t dbase = tmem_base + b * p.acc_cols;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          for (int plane = 0; plane < 2; ++plane, ++it) {
+            const int s = it % p.S;
+            ptx::mbar_wait(&bars->full[s], (it / p.S) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
+              const uint32_t wbase = plane ? (ptx::smem_u32(s_wB + (size_t)kb * T * tapB) >> 4) | (1u << 16)
+                                           : (ptx::smem_u32(s_wA + (size_t)kb * T * tapA) >> 4) | (1u << 16);
+              uint32_t sp = 0, fresh_left = (plane == 0 && kb == 0) ? (uint32_t)p.nsplit : 0u;
+              u16_issue_plane<MODE, true>(p, abase, wbase, dbase + (plane ? (uint32_t)NPAD : 0u), pairw,
+                                          plane ? idesc_lo : idesc_st, a_hi32, w_hi32, (plane ? tapB : tapA) >> 4, ksteps, smask,
+                                          sp, fresh_left, plane == 0 && kb == 0);
+            }
+            __syncwarp();
+            if (ptx::elect_one()) ptx::tc_commit2(&bars->empty[s]);
+            __syncwarp();
+          }
+        }
+        if (ptx::elect_one()) ptx::tc_commit2(&bars->acc_full[b]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs, own tile, own TMEM) =====
+    const int q4 = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int m = q4 * 32 + lane;
+    const int grp = m >> 3, xx = m & 7;
+    const int hh = grp / p.bn, nb = grp % p.bn;
+    int h_ones = 0, h_valid = 0;
+    uint32_t ti = 0;
+    for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
+      const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
+      const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+      ptx::mbar_wait(&bars->acc_full[b], use & 1);
+      ptx::tc_fence_after();
+      long long tt = 2 * tp + rank;
+      const int tx = (int)(tt % p.tiles_x);
+      tt /= p.tiles_x;
+      const int ty = (int)(tt % p.tiles_y);
+      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
+      const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
+      const bool valid = n < p.n;
+      const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
+      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_leader(&bars->acc_empty[b]);
+    }
+    if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
+      if (a.q == 2) {
+        h_ones = __reduce_add_sync(0xffffffffu, h_ones);
+        h_valid = __reduce_add_sync(0xffffffffu, h_valid);
+        if (lane == 0) {
+          if (h_ones) atomicAdd(&s_hist[1], (unsigned)h_ones);
+          if (h_valid - h_ones) atomicAdd(&s_hist[0], (unsigned)(h_valid - h_ones));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = tid - 128; i < a.q; i += 256)
+        if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // neither CTA may leave (or free TMEM) while the pair still has MMAs / remote arrives in flight
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, 512);
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 inline int u16_mode_of(int kind, int stride) { return kind == 1 ? U16_DECONV : (stride == 2 ? U16_S2 : U16_S1); }
 
@@ -645,6 +889,20 @@ inline cudaError_t u16_launch_t(cudaStream_t stream, const CUtensorMap& th, cons
   return cudaGetLastError();
 }
 
+template <int MODE>
+inline cudaError_t u16_launch_pair_t(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
+                                     const LayerArgs& a, int grid, size_t smem) {
+  auto k = u16_pair_kernel<MODE>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  k<<<grid, kU16Threads, smem, stream>>>(th, tl, p, a);  // __cluster_dims__(2, 1, 1): grid is even
+  return cudaGetLastError();
+}
+
 struct U16Plan {
   int cs;      // output channels per slice
   U16Params p;
@@ -652,8 +910,9 @@ struct U16Plan {
 };
 
 // Geometry + shared-memory plan for one slice width; returns false if it does not fit.
-inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out) {
+inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out, bool pair = false) {
   U16Params p{};
+  p.pair = pair ? 1 : 0;
   p.mode = u16_mode_of(kind, stride);
   p.n = a.n;
   p.Ht = p.mode == U16_DECONV ? a.hin : a.hout;
@@ -726,27 +985,33 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   p.slot_bytes = p.box_stride * (uint32_t)p.nbox;
   p.tap_bytes = 2u * (uint32_t)p.npad * wrow;
   p.w_bytes = (uint32_t)p.KB * (p.mode == U16_DECONV_PH ? 4u : 9u) * p.tap_bytes;
+  if (pair) {
+    // each CTA of the pair keeps half of every stacked tile plus half of W_hi
+    p.wA_bytes = p.w_bytes / 2;
+    p.wB_bytes = p.w_bytes / 4;
+    p.w_bytes = ((p.wA_bytes + 1023u) & ~1023u) + ((p.wB_bytes + 1023u) & ~1023u);
+  }
   // TMEM: conv nsplit pairs x 2 buffers; deconv 4 phase pairs
-  const int pair = 2 * p.npad;
+  const int accw = 2 * p.npad;  // one (D_main | D_lo) accumulator pair
   if (p.mode == U16_DECONV_PH) {
     p.nsplit = 1;
-    p.acc_cols = (uint32_t)pair;
+    p.acc_cols = (uint32_t)accw;
     p.nbuf = 2;
   } else if (p.mode == U16_DECONV) {
     p.nsplit = 1;
-    p.acc_cols = 4u * pair;
+    p.acc_cols = 4u * accw;
     if (p.acc_cols > 512) return false;
     p.nbuf = p.acc_cols * 2 <= 512 ? 2 : 1;
   } else {
-    if (pair > 512) return false;
-    p.nbuf = pair * 2 <= 512 ? 2 : 1;
+    if (accw > 512) return false;
+    p.nbuf = accw * 2 <= 512 ? 2 : 1;
     // the tensor core truncates when adding into the accumulator: keep <= ~18 accumulation steps per
     // accumulator (what a 32-channel layer has unsplit), power of two, as TMEM allows
     const int steps = p.KB * 9 * p.ksteps;
-    const int cap = (512 / p.nbuf) / pair;
+    const int cap = (512 / p.nbuf) / accw;
     p.nsplit = 1;
     while (p.nsplit * 2 <= cap && p.nsplit < 4 && steps > 18 * p.nsplit) p.nsplit *= 2;
-    p.acc_cols = (uint32_t)(p.nsplit * pair);
+    p.acc_cols = (uint32_t)(p.nsplit * accw);
   }
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
   const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
@@ -768,12 +1033,17 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
   auto encode = umma_encode_fn();
   if (!encode) return fail("cuTensorMapEncodeTiled is unavailable (driver too old?)", -2);
   // widest output-channel slice whose weights stay resident
+  static const bool pair_enabled = [] {
+    const char* e = getenv("TIC_U16_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  const bool pair = pair_enabled && num_sms >= 2;
   U16Plan plan{};
   int cs = std::min(a.cout, 128);
   cs = (cs + 15) / 16 * 16;
   bool ok = false;
   for (; cs >= 16; cs -= 16)
-    if ((ok = u16_plan(a, kind, stride, std::min(cs, a.cout), &plan))) break;
+    if ((ok = u16_plan(a, kind, stride, std::min(cs, a.cout), &plan, pair))) break;
   if (!ok) return fail("layer does not fit the fp16-pair tensor path", -5);
   cs = plan.cs;
 
@@ -810,34 +1080,52 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
     if (si >= 16) return fail("too many output-channel slices", -5);
     const int csl = std::min(cs, a.cout - oc0);
     U16Plan pl{};
-    if (!u16_plan(a, kind, stride, csl, &pl)) return fail("slice plan failed", -5);
+    if (!u16_plan(a, kind, stride, csl, &pl, pair)) return fail("slice plan failed", -5);
     U16Params p = pl.p;
     p.oc0 = oc0;
     U16WeightSlice* ws = &uw->slice[si];
-    if (!ws->img || ws->bytes != p.w_bytes || ws->mode != p.mode || ws->npad != p.npad || ws->oc0 != oc0) {
+    const size_t img_bytes = pair ? 2 * (size_t)p.w_bytes : (size_t)p.w_bytes;
+    if (!ws->img || ws->bytes != img_bytes || ws->mode != p.mode || ws->npad != p.npad || ws->oc0 != oc0 || ws->pair != p.pair) {
       ws->release();
-      if (cudaMalloc(&ws->img, p.w_bytes) != cudaSuccess) return fail("cudaMalloc for weight images failed", -4);
-      ws->bytes = p.w_bytes;
+      if (cudaMalloc(&ws->img, img_bytes) != cudaSuccess) return fail("cudaMalloc for weight images failed", -4);
+      ws->bytes = img_bytes;
       ws->mode = p.mode;
       ws->npad = p.npad;
       ws->oc0 = oc0;
-      if (p.mode == U16_DECONV_PH)
+      ws->pair = p.pair;
+      if (pair)
+        u16_build_weights_pair_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.cpad, p.mode == U16_DECONV_PH,
+                                                              p.kc, p.KB, (p.wA_bytes + 1023u) & ~1023u,
+                                                              (p.wB_bytes + 1023u) & ~1023u, ws->img);
+      else if (p.mode == U16_DECONV_PH)
         u16_build_weights_ph_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.cpad, p.kc, p.KB, ws->img);
       else
         u16_build_weights_kernel<<<64, 256, 0, stream>>>(w_dev, a.cin, a.cout, oc0, csl, p.npad, p.kc, p.KB, ws->img);
       if (cudaGetLastError() != cudaSuccess) return fail("weight image kernel failed", -2);
     }
     p.wimg = ws->img;
-    const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
     cudaError_t e;
-    if (p.mode == U16_S1)
-      e = u16_launch_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
-    else if (p.mode == U16_S2)
-      e = u16_launch_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
-    else if (p.mode == U16_DECONV_PH)
-      e = u16_launch_t<U16_DECONV_PH>(stream, tm[0], tm[1], p, a, grid, pl.smem);
-    else
-      e = u16_launch_t<U16_DECONV>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    if (pair) {
+      const int grid = 2 * (int)std::min<long long>((p.num_tiles + 1) / 2, num_sms / 2);
+      if (p.mode == U16_S1)
+        e = u16_launch_pair_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else if (p.mode == U16_S2)
+        e = u16_launch_pair_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else if (p.mode == U16_DECONV_PH)
+        e = u16_launch_pair_t<U16_DECONV_PH>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else
+        e = u16_launch_pair_t<U16_DECONV>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    } else {
+      const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
+      if (p.mode == U16_S1)
+        e = u16_launch_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else if (p.mode == U16_S2)
+        e = u16_launch_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else if (p.mode == U16_DECONV_PH)
+        e = u16_launch_t<U16_DECONV_PH>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else
+        e = u16_launch_t<U16_DECONV>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+    }
     if (e != cudaSuccess) return fail(std::string("fp16-pair tensor launch failed: ") + cudaGetErrorString(e), -2);
     if (launches) ++*launches;
   }

@@ -60,8 +60,10 @@ struct tic_codec {
   int mode = TIC_COMPUTE_FP32;
   int chunk128 = 4096;
   // workspaces
-  float* act[3] = {nullptr, nullptr, nullptr};
+  float* act[3] = {nullptr, nullptr, nullptr};  // rotating (sub-)chunk activations
   size_t act_bytes = 0;
+  float* bnd[2] = {nullptr, nullptr};           // chunk-level tensors at layer-group boundaries
+  size_t bnd_bytes = 0;
   void* stage_in[2] = {nullptr, nullptr};
   void* stage_out[2] = {nullptr, nullptr};
   size_t stage_in_bytes = 0, stage_out_bytes = 0;
@@ -254,14 +256,120 @@ int check_graph_ready(tic_codec* h, int gi, bool need_norm) {
   return TIC_OK;
 }
 
+// Layer groups of one graph execution (fp16-pair mode).  With every layer at (or near) the HBM roofline the
+// remaining lever is to keep inter-layer tensors in the 126 MB L2: consecutive layers run over a SUB-chunk of
+// m patches so that the tensors between them (m x bytes per patch) fit the L2 budget, and only the tensor at a
+// group boundary is written out for the whole chunk.  A group is closed when the next layer would push m so
+// low that some layer of the group could not fill the 148 SMs twice (model_0: {encode_0, encode_1} at m = 111
+// and {encode_2 .. encode_4} at m = 888; decoder {decode_4 .. decode_2} and {decode_1, decode_0}).
+struct LayerShape {
+  int hin, win, cin, hout, wout, cout, pad_t, pad_l;
+};
+struct LayerGroup {
+  int first, last, m;
+};
+
+long long l2_budget_bytes_per_group() {
+  static const long long mb = [] {
+    // 0 (default) disables grouping.  Measured on B200 (model_0, 12288 patches): 56 MB -> 20.3 ms per encode+decode
+    // step against 14.0 ms ungrouped: each extra (20 us) launch costs ~8 us of prologue (weight tiles, TMEM,
+    // cluster sync) and tail.  The schedule pays off only once a group runs as one persistent kernel.
+    const char* e = getenv("TIC_L2_BUDGET_MB");
+    const long long v = e ? atoll(e) : 0;
+    return v < 0 ? 0 : std::min<long long>(v, 4096);
+  }();
+  return mb << 20;
+}
+
+std::vector<LayerGroup> plan_groups(const Graph& g, const std::vector<LayerShape>& sh, int L, int n, bool enable) {
+  std::vector<LayerGroup> groups;
+  const long long budget = l2_budget_bytes_per_group();
+  if (!enable || budget <= 0 || n < 64) {
+    groups.push_back({0, L - 1, n});
+    return groups;
+  }
+  auto tiles_pp = [&](int i) {
+    const bool dc = g.layers[i].d.kind == TIC_DECONV;
+    return (double)(dc ? sh[i].hin * sh[i].win : sh[i].hout * sh[i].wout) / 128.0;
+  };
+  auto out_bytes = [&](int i) { return (long long)sh[i].hout * sh[i].wout * sh[i].cout * 4; };
+  const double min_tiles = 296.0;  // two tiles per SM (one CTA pair per TPC, twice)
+  int first = 0;
+  while (first < L) {
+    int last = first;
+    long long tmax = 0;
+    bool in_res = g.layers[first].d.res_begin && !g.layers[first].d.res_end;
+    while (last + 1 < L) {
+      const long long tnew = std::max(tmax, out_bytes(last));
+      const long long mnew = std::min<long long>(n, std::max<long long>(1, budget / std::max<long long>(tnew, 1)));
+      bool ok = true;
+      if (mnew < n)
+        for (int j = first; j <= last + 1; ++j) ok = ok && tiles_pp(j) * (double)mnew >= min_tiles;
+      if (!ok && !in_res) break;
+      ++last;
+      tmax = tnew;
+      if (g.layers[last].d.res_begin) in_res = true;
+      if (g.layers[last].d.res_end) in_res = false;
+    }
+    long long m = tmax > 0 ? std::min<long long>(n, std::max<long long>(1, budget / tmax)) : n;
+    if (m < n) {
+      // a whole number of waves for the layer with the fewest tiles: m a multiple of q patches
+      double tp_min = 1e30;
+      for (int j = first; j <= last; ++j) tp_min = std::min(tp_min, tiles_pp(j));
+      const long long q = std::max<long long>(1, (long long)(296.0 / tp_min + 0.5));
+      long long mr = ((m + q / 2) / q) * q;
+      if (mr < q) mr = q;
+      if (mr * tmax > budget + budget / 4) mr = std::max<long long>(q, (m / q) * q);
+      m = std::min<long long>(n, mr);
+    }
+    groups.push_back({first, last, (int)m});
+    first = last + 1;
+  }
+  return groups;
+}
+
+int ensure_buffers(tic_codec* h, float** bufs, int count, size_t* have, size_t need) {
+  if (need <= *have) return TIC_OK;
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < count; ++i) {
+    if (bufs[i]) cudaFree(bufs[i]);
+    bufs[i] = nullptr;
+  }
+  *have = 0;
+  for (int i = 0; i < count; ++i) {
+    cudaError_t e = cudaMalloc((void**)&bufs[i], need);
+    if (e != cudaSuccess) return fail(h, TIC_ERR_NOMEM, "cudaMalloc(%zu) for activations failed: %s", need, cudaGetErrorString(e));
+  }
+  *have = need;
+  return TIC_OK;
+}
+
 // Run graph gi over n patches whose first-layer input map is h0 x w0 x c0.
 int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, int n, int h0, int w0, int limit = -1) {
   Graph& g = h->g[gi];
   const int L = limit > 0 ? std::min(limit, (int)g.layers.size()) : (int)g.layers.size();
-  Shape s{h0, w0, g.layers[0].d.cin};
-  size_t mx = 0;
-  Shape so;
-  if (graph_out_shape(g, s, &so, &mx, limit) != 0) return fail(h, TIC_ERR_INVALID, "layer channel chain is inconsistent");
+  std::vector<LayerShape> sh(L);
+  {
+    Shape s{h0, w0, g.layers[0].d.cin};
+    for (int i = 0; i < L; ++i) {
+      const tic_layer_desc& d = g.layers[i].d;
+      if (d.cin != s.c) return fail(h, TIC_ERR_INVALID, "layer channel chain is inconsistent");
+      LayerShape& t = sh[i];
+      t.hin = s.h;
+      t.win = s.w;
+      t.cin = s.c;
+      t.pad_t = t.pad_l = 0;
+      if (d.kind == TIC_CONV) {
+        same_pad(s.h, d.stride, &t.hout, &t.pad_t);
+        same_pad(s.w, d.stride, &t.wout, &t.pad_l);
+      } else {
+        t.hout = 2 * s.h;
+        t.wout = 2 * s.w;
+      }
+      t.cout = d.cout;
+      s = Shape{t.hout, t.wout, t.cout};
+    }
+  }
   const bool pair16 = h->mode == TIC_COMPUTE_TENSOR_F16X3;  // intermediate activations are fp16 pair planes
   // pair mode: f32 / symbol inputs of a tensor-capable first layer are split into a workspace buffer first
   bool split_input = false;
@@ -269,149 +377,168 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
     LayerArgs t{};
     const tic_layer_desc& d0 = g.layers[0].d;
     t.n = n;
-    t.hin = s.h;
-    t.win = s.w;
-    t.cin = s.c;
-    int pb;
-    if (d0.kind == TIC_CONV) {
-      same_pad(s.h, d0.stride, &t.hout, &pb);
-      same_pad(s.w, d0.stride, &t.wout, &pb);
-    } else {
-      t.hout = 2 * s.h;
-      t.wout = 2 * s.w;
-    }
-    t.cout = d0.cout;
+    t.hin = sh[0].hin;
+    t.win = sh[0].win;
+    t.cin = sh[0].cin;
+    t.hout = sh[0].hout;
+    t.wout = sh[0].wout;
+    t.cout = sh[0].cout;
     t.in_mode = IO_ACT16;
     t.out_mode = L == 1 ? io_out.mode : IO_ACT16;
     split_input = u16_supported(t, d0.kind, d0.stride);
   }
-  if (split_input) mx = std::max(mx, (size_t)s.h * s.w * s.c);
-  const size_t need = mx * (size_t)n * sizeof(float);
-  if (need > h->act_bytes) {
-    TIC_CUDA(h, cudaStreamSynchronize(h->stream));
-    for (int i = 0; i < 3; ++i) {
-      if (h->act[i]) cudaFree(h->act[i]);
-      h->act[i] = nullptr;
-    }
-    h->act_bytes = 0;
-    for (int i = 0; i < 3; ++i) {
-      cudaError_t e = cudaMalloc((void**)&h->act[i], need);
-      if (e != cudaSuccess) return fail(h, TIC_ERR_NOMEM, "cudaMalloc(%zu) for activations failed: %s", need, cudaGetErrorString(e));
-    }
-    h->act_bytes = need;
+  const std::vector<LayerGroup> groups = plan_groups(g, sh, L, n, pair16);
+  // workspaces: three rotating sub-chunk buffers, two chunk-level group-boundary buffers
+  size_t intra = 0, bnd = 0;
+  for (size_t gx = 0; gx < groups.size(); ++gx) {
+    const LayerGroup& G = groups[gx];
+    for (int i = G.first; i < G.last; ++i) intra = std::max(intra, (size_t)G.m * sh[i].hout * sh[i].wout * sh[i].cout);
+    if (gx == 0 && split_input) intra = std::max(intra, (size_t)G.m * sh[0].hin * sh[0].win * sh[0].cin);
+    if (gx + 1 < groups.size()) bnd = std::max(bnd, (size_t)n * sh[G.last].hout * sh[G.last].wout * sh[G.last].cout);
   }
-  int cur = -1;            // buffer index holding the current activation (-1: caller input)
-  int res_buf = -1;        // buffer holding the residual source
-  if (split_input) {
-    const long long count = (long long)n * s.h * s.w * s.c;
-    __half* hi = reinterpret_cast<__half*>(h->act[0]);
-    const int blocks = (int)std::min<long long>((count + 255) / 256, (long long)h->num_sms * 8);
-    if (io_in.mode == IO_ACT)
-      u16_split_f32_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const float*>(io_in.in), hi, hi + count, count);
-    else
-      u16_split_symlut_kernel<<<blocks, 256, 0, h->stream>>>(
-          reinterpret_cast<const uint8_t*>(io_in.in) + (long long)io_in.geo.n0 * s.h * s.w * s.c, h->d_symlut, hi, hi + count, count);
-    h->launches++;
-    TIC_CUDA(h, cudaGetLastError());
-    cur = 0;
-  }
-  for (int i = 0; i < L; ++i) {
-    Layer& ly = g.layers[i];
-    const tic_layer_desc& d = ly.d;
-    LayerArgs a{};
-    a.n = n;
-    a.hin = s.h;
-    a.win = s.w;
-    a.cin = s.c;
-    if (d.kind == TIC_CONV) {
-      same_pad(s.h, d.stride, &a.hout, &a.pad_t);
-      same_pad(s.w, d.stride, &a.wout, &a.pad_l);
-    } else {
-      a.hout = 2 * s.h;
-      a.wout = 2 * s.w;
-    }
-    a.cout = d.cout;
-    a.act = d.act;
-    a.wgt = ly.w;
-    a.bias = ly.b;
-    a.q = h->q;
-    a.hist = h->d_hist;
-    for (int c = 0; c < 3; ++c) {
-      a.mean[c] = g.mean[c];
-      a.stdv[c] = g.stdv[c];
-    }
-    // input
-    if (i == 0 && !split_input) {
-      a.in = io_in.in;
-      a.in_mode = io_in.mode;
-      a.geo = io_in.geo;
-      a.lut = (io_in.mode == IO_U8_NORM) ? g.d_normlut : (io_in.mode == IO_U8_SYMLUT ? h->d_symlut : nullptr);
-    } else {
-      a.in = h->act[cur];
-      a.in_mode = pair16 ? IO_ACT16 : IO_ACT;
-      a.in_lo_off = (long long)n * a.hin * a.win * a.cin;
-    }
-    if (d.res_begin) res_buf = cur;
-    // output buffer: any workspace buffer that is neither the input nor the live residual
-    int ob = -1;
-    if (i == L - 1) {
-      a.out = io_out.out;
-      a.out_mode = io_out.mode;
-      if (i == 0) {
-        // single-layer graph: geo is shared by prologue and epilogue only if both need it
-        if (io_out.mode != IO_ACT) a.geo = io_out.geo;
-      } else {
-        a.geo = io_out.geo;
+  int rc0 = ensure_buffers(h, h->act, 3, &h->act_bytes, intra * sizeof(float));
+  if (rc0 != TIC_OK) return rc0;
+  rc0 = ensure_buffers(h, h->bnd, 2, &h->bnd_bytes, bnd * sizeof(float));
+  if (rc0 != TIC_OK) return rc0;
+
+  for (size_t gx = 0; gx < groups.size(); ++gx) {
+    const LayerGroup& G = groups[gx];
+    const bool first_group = gx == 0, last_group = gx + 1 == groups.size();
+    for (int s0 = 0; s0 < n; s0 += G.m) {
+      const int ns = std::min(G.m, n - s0);
+      int cur = -1;        // act[] index holding the current activation (-1: the group's input)
+      int res_buf = -1;    // act[] index of the live residual source (-1: none, or not an act[] buffer)
+      const void* res_ptr = nullptr;
+      long long res_lo = 0;
+      if (first_group && split_input) {
+        const long long per = (long long)sh[0].hin * sh[0].win * sh[0].cin;
+        const long long count = (long long)ns * per;
+        __half* hi = reinterpret_cast<__half*>(h->act[0]);
+        const int blocks = (int)std::min<long long>((count + 255) / 256, (long long)h->num_sms * 8);
+        if (io_in.mode == IO_ACT)
+          u16_split_f32_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const float*>(io_in.in) + (long long)s0 * per, hi,
+                                                             hi + count, count);
+        else
+          u16_split_symlut_kernel<<<blocks, 256, 0, h->stream>>>(
+              reinterpret_cast<const uint8_t*>(io_in.in) + ((long long)io_in.geo.n0 + s0) * per, h->d_symlut, hi, hi + count, count);
+        h->launches++;
+        TIC_CUDA(h, cudaGetLastError());
+        cur = 0;
       }
-    } else {
-      for (int b = 0; b < 3; ++b)
-        if (b != cur && b != res_buf) {
-          ob = b;
-          break;
+      for (int i = G.first; i <= G.last; ++i) {
+        Layer& ly = g.layers[i];
+        const tic_layer_desc& d = ly.d;
+        const LayerShape& t = sh[i];
+        LayerArgs a{};
+        a.n = ns;
+        a.hin = t.hin;
+        a.win = t.win;
+        a.cin = t.cin;
+        a.hout = t.hout;
+        a.wout = t.wout;
+        a.cout = t.cout;
+        a.pad_t = t.pad_t;
+        a.pad_l = t.pad_l;
+        a.act = d.act;
+        a.wgt = ly.w;
+        a.bias = ly.b;
+        a.q = h->q;
+        a.hist = h->d_hist;
+        for (int c = 0; c < 3; ++c) {
+          a.mean[c] = g.mean[c];
+          a.stdv[c] = g.stdv[c];
         }
-      a.out = h->act[ob];
-      a.out_mode = pair16 ? IO_ACT16 : IO_ACT;
-      a.out_lo_off = (long long)n * a.hout * a.wout * a.cout;
+        const long long ein = (long long)t.hin * t.win * t.cin, eout = (long long)t.hout * t.wout * t.cout;
+        // ---- input
+        if (i == G.first && cur < 0) {
+          if (first_group) {
+            a.in_mode = io_in.mode;
+            a.geo = io_in.geo;
+            a.geo.n0 += s0;
+            a.lut = (io_in.mode == IO_U8_NORM) ? g.d_normlut : (io_in.mode == IO_U8_SYMLUT ? h->d_symlut : nullptr);
+            a.in = io_in.mode == IO_ACT ? (const void*)(reinterpret_cast<const float*>(io_in.in) + (long long)s0 * ein) : io_in.in;
+          } else {
+            a.in = reinterpret_cast<const __half*>(h->bnd[(gx - 1) & 1]) + (long long)s0 * ein;
+            a.in_mode = IO_ACT16;
+            a.in_lo_off = (long long)n * ein;
+          }
+        } else {
+          a.in = h->act[cur];
+          a.in_mode = pair16 ? IO_ACT16 : IO_ACT;
+          a.in_lo_off = (long long)ns * ein;
+        }
+        if (d.res_begin) {
+          res_buf = cur;
+          res_ptr = a.in;
+          res_lo = a.in_lo_off;
+        }
+        // ---- output: a workspace buffer that is neither the input nor the live residual
+        int ob = -1;
+        if (i == G.last) {
+          if (last_group) {
+            a.out_mode = io_out.mode;
+            a.out = io_out.mode == IO_ACT ? (void*)(reinterpret_cast<float*>(io_out.out) + (long long)s0 * eout) : io_out.out;
+            // a single-layer graph shares one geo between prologue and epilogue only if both need it
+            if (!(first_group && i == G.first && io_out.mode == IO_ACT)) {
+              a.geo = io_out.geo;
+              a.geo.n0 += s0;
+            }
+          } else {
+            a.out = reinterpret_cast<__half*>(h->bnd[gx & 1]) + (long long)s0 * eout;
+            a.out_mode = IO_ACT16;
+            a.out_lo_off = (long long)n * eout;
+          }
+        } else {
+          for (int b = 0; b < 3; ++b)
+            if (b != cur && b != res_buf) {
+              ob = b;
+              break;
+            }
+          a.out = h->act[ob];
+          a.out_mode = pair16 ? IO_ACT16 : IO_ACT;
+          a.out_lo_off = (long long)ns * eout;
+        }
+        if (d.res_end) {
+          if (!res_ptr) return fail(h, TIC_ERR_INVALID, "res_end without res_begin at layer %d", i);
+          a.res = reinterpret_cast<const float*>(res_ptr);
+          a.res16 = pair16 ? 1 : 0;
+          a.res_lo_off = res_lo;
+        }
+        int rc;
+        tic_codec::ProfRec pr{gi, i, nullptr, nullptr};
+        if (h->profile) {
+          cudaEventCreate(&pr.e0);
+          cudaEventCreate(&pr.e1);
+          cudaEventRecord(pr.e0, h->stream);
+        }
+        if (pair16 && f16_first_supported(a, d.kind, d.stride)) {
+          int nl = 0;
+          rc = launch_first16(h->stream, a, d.stride, ly.w, &ly.fw16, h->num_sms, &h->err, &nl);
+          h->launches += nl;
+        } else if (pair16 && u16_supported(a, d.kind, d.stride)) {
+          int nl = 0;
+          rc = launch_u16(h->stream, a, d.kind, d.stride, ly.w, &ly.uw16, h->num_sms, &h->err, &nl);
+          h->launches += nl;
+        } else if (h->mode != TIC_COMPUTE_FP32 && !pair16 && umma_supported(a, d.kind, d.stride)) {
+          int nl = 0;
+          rc = launch_umma(h->stream, a, d.kind, d.stride, ly.w, &ly.uw, h->mode == TIC_COMPUTE_TENSOR_3XTF32, h->num_sms,
+                           &h->err, &nl);
+          h->launches += nl;
+        } else {
+          rc = launch_simt(h, a, d.kind, d.stride);
+        }
+        if (h->profile) {
+          cudaEventRecord(pr.e1, h->stream);
+          h->prof_pending.push_back(pr);
+        }
+        if (rc != TIC_OK) return rc < 0 && rc >= TIC_ERR_UNSUPPORTED ? rc : TIC_ERR_CUDA;
+        if (d.res_end) {
+          res_buf = -1;
+          res_ptr = nullptr;
+        }
+        cur = ob;
+      }
     }
-    if (d.res_end) {
-      if (res_buf < 0) return fail(h, TIC_ERR_INVALID, "res_end without res_begin at layer %d", i);
-      a.res = h->act[res_buf];
-      a.res16 = pair16 ? 1 : 0;
-      a.res_lo_off = (long long)n * a.hout * a.wout * a.cout;
-    }
-    int rc;
-    tic_codec::ProfRec pr{gi, i, nullptr, nullptr};
-    if (h->profile) {
-      cudaEventCreate(&pr.e0);
-      cudaEventCreate(&pr.e1);
-      cudaEventRecord(pr.e0, h->stream);
-    }
-    if (pair16 && f16_first_supported(a, d.kind, d.stride)) {
-      int nl = 0;
-      rc = launch_first16(h->stream, a, d.stride, ly.w, &ly.fw16, h->num_sms, &h->err, &nl);
-      h->launches += nl;
-    } else if (pair16 && u16_supported(a, d.kind, d.stride)) {
-      int nl = 0;
-      rc = launch_u16(h->stream, a, d.kind, d.stride, ly.w, &ly.uw16, h->num_sms, &h->err, &nl);
-      h->launches += nl;
-    } else if (h->mode != TIC_COMPUTE_FP32 && !pair16 && umma_supported(a, d.kind, d.stride)) {
-      int nl = 0;
-      rc = launch_umma(h->stream, a, d.kind, d.stride, ly.w, &ly.uw, h->mode == TIC_COMPUTE_TENSOR_3XTF32,
-                       h->num_sms, &h->err, &nl);
-      h->launches += nl;
-    } else {
-      rc = launch_simt(h, a, d.kind, d.stride);
-    }
-    if (h->profile) {
-      cudaEventRecord(pr.e1, h->stream);
-      h->prof_pending.push_back(pr);
-    }
-    if (rc != TIC_OK) return rc;
-    if (d.res_end) res_buf = -1;
-    cur = ob;
-    s.h = a.hout;
-    s.w = a.wout;
-    s.c = a.cout;
   }
   return TIC_OK;
 }
@@ -587,6 +714,8 @@ void tic_destroy(tic_codec* h) {
   }
   for (int i = 0; i < 3; ++i)
     if (h->act[i]) cudaFree(h->act[i]);
+  for (int i = 0; i < 2; ++i)
+    if (h->bnd[i]) cudaFree(h->bnd[i]);
   for (int b = 0; b < 2; ++b) {
     if (h->stage_in[b]) cudaFree(h->stage_in[b]);
     if (h->stage_out[b]) cudaFree(h->stage_out[b]);

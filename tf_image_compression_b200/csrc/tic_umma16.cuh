@@ -296,6 +296,9 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
                                                   const int half, const float* s_bias, unsigned* s_hist, int& h_ones,
                                                   int& h_valid, const int cpad = 0) {
   constexpr bool kDeconv = MODE == U16_DECONV || MODE == U16_DECONV_PH;
+#ifdef TIC_DEBUG_SKIP_EPILOGUE  // measurement aid: time the kernels without their epilogue work
+  return;
+#endif
   if (MODE == U16_DECONV_PH && cpad == 4) {
     // 3-channel last layer: the 16 columns are (phase, channel) of the 2x2 output pixels of this input pixel;
     // the two warps of a lane quadrant take the even / the odd output row

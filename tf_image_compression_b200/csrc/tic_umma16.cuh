@@ -353,46 +353,91 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
     const long long pix0 = ((long long)n * a.hout + (kDeconv ? 2 * yt : yt)) * a.wout + (kDeconv ? 2 * xt : xt);
     __half* const obase = reinterpret_cast<__half*>(a.out) + pix0 * a.cout + oc0;
     const __half* const rbase = a.res ? reinterpret_cast<const __half*>(a.res) + pix0 * a.cout + oc0 : nullptr;
-    for (int ph = 0; ph < phases; ++ph) {
-      const int poff = kDeconv ? ((ph >> 1) * a.wout + (ph & 1)) * a.cout : 0;
-      for (int c = half * 16; c < cend; c += 32) {
-        float v[16];
-        u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
-        if (!valid || oc0 + c >= a.cout) continue;
-        const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
+    // bias + activation (+ residual) + split + the four 16-byte stores of one 16-channel chunk
+    auto finish = [&](float (&v)[16], const int c, const int poff) {
+      const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b = bp[i];
-          v[4 * i] = fmaxf(__fadd_rn(v[4 * i], b.x), floor_v);
-          v[4 * i + 1] = fmaxf(__fadd_rn(v[4 * i + 1], b.y), floor_v);
-          v[4 * i + 2] = fmaxf(__fadd_rn(v[4 * i + 2], b.z), floor_v);
-          v[4 * i + 3] = fmaxf(__fadd_rn(v[4 * i + 3], b.w), floor_v);
-        }
-        if (rbase) {
-          const uint4* rh = reinterpret_cast<const uint4*>(rbase + poff + c);
-          const uint4* rl = reinterpret_cast<const uint4*>(rbase + a.res_lo_off + poff + c);
+      for (int i = 0; i < 4; ++i) {
+        const float4 b = bp[i];
+        v[4 * i] = fmaxf(__fadd_rn(v[4 * i], b.x), floor_v);
+        v[4 * i + 1] = fmaxf(__fadd_rn(v[4 * i + 1], b.y), floor_v);
+        v[4 * i + 2] = fmaxf(__fadd_rn(v[4 * i + 2], b.z), floor_v);
+        v[4 * i + 3] = fmaxf(__fadd_rn(v[4 * i + 3], b.w), floor_v);
+      }
+      if (rbase) {
+        const uint4* rh = reinterpret_cast<const uint4*>(rbase + poff + c);
+        const uint4* rl = reinterpret_cast<const uint4*>(rbase + a.res_lo_off + poff + c);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint4 qh = __ldg(rh + j), ql = __ldg(rl + j);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+        for (int j = 0; j < 2; ++j) {
+          const uint4 qh = __ldg(rh + j), ql = __ldg(rl + j);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
+          const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
-              v[8 * j + 2 * e] = __fadd_rn(__fmaf_rn(lf.x, 1.0f / 2048.0f, hf.x), v[8 * j + 2 * e]);
-              v[8 * j + 2 * e + 1] = __fadd_rn(__fmaf_rn(lf.y, 1.0f / 2048.0f, hf.y), v[8 * j + 2 * e + 1]);
-            }
+          for (int e = 0; e < 4; ++e) {
+            const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+            v[8 * j + 2 * e] = __fadd_rn(__fmaf_rn(lf.x, 1.0f / 2048.0f, hf.x), v[8 * j + 2 * e]);
+            v[8 * j + 2 * e + 1] = __fadd_rn(__fmaf_rn(lf.y, 1.0f / 2048.0f, hf.y), v[8 * j + 2 * e + 1]);
           }
         }
-        uint32_t hp[8], lp[8];
+      }
+      uint32_t hp[8], lp[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
-        uint4* oh = reinterpret_cast<uint4*>(obase + poff + c);
-        uint4* ol = reinterpret_cast<uint4*>(obase + a.out_lo_off + poff + c);
-        oh[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        oh[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
-        ol[0] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
-        ol[1] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+      for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
+      uint4* oh = reinterpret_cast<uint4*>(obase + poff + c);
+      uint4* ol = reinterpret_cast<uint4*>(obase + a.out_lo_off + poff + c);
+      oh[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      oh[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
+      ol[0] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      ol[1] = make_uint4(lp[4], lp[5], lp[6], lp[7]);
+    };
+    // units (phase, 16-channel chunk) alternate between the two warps of a lane quadrant; a warp works on two
+    // of its units at once (all four TMEM loads first, one wait, two independent instruction streams)
+    const int nch = cend >> 4, U = phases * nch;
+    auto unit_t = [&](int u, int& c, int& poff) -> uint32_t {
+      const int ph = u / nch;
+      c = (u - ph * nch) << 4;
+      poff = kDeconv ? ((ph >> 1) * a.wout + (ph & 1)) * a.cout : 0;
+      return tbuf + (MODE == U16_DECONV_PH ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
+    };
+    if (kDeconv || nsplit == 1) {
+      for (int u = half; u < U; u += 4) {
+        int cA, pA, cB = 0, pB = 0;
+        const uint32_t tA = unit_t(u, cA, pA);
+        const bool hasB = u + 2 < U;
+        float va[16], la[16];
+        if (hasB) {
+          const uint32_t tB = unit_t(u + 2, cB, pB);
+          float vb[16], lb[16];
+          ptx::tmem_ld16_nowait(tA + NPAD, la);
+          ptx::tmem_ld16_nowait(tA, va);
+          ptx::tmem_ld16_nowait(tB + NPAD, lb);
+          ptx::tmem_ld16_nowait(tB, vb);
+          ptx::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              va[i] = __fmaf_rn(la[i], 1.0f / 2048.0f, va[i]);
+              vb[i] = __fmaf_rn(lb[i], 1.0f / 2048.0f, vb[i]);
+            }
+            finish(va, cA, pA);
+            finish(vb, cB, pB);
+          }
+        } else {
+          ptx::tmem_ld16_nowait(tA + NPAD, la);
+          ptx::tmem_ld16_nowait(tA, va);
+          ptx::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) va[i] = __fmaf_rn(la[i], 1.0f / 2048.0f, va[i]);
+            finish(va, cA, pA);
+          }
+        }
+      }
+    } else {
+      for (int c = half * 16; c < cend; c += 32) {
+        float v[16];
+        u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, 0, c, cpad);
+        if (valid) finish(v, c, 0);
       }
     }
     return;

@@ -1,0 +1,124 @@
+"""Host entropy coder (tf_image_compression_b200.range_coder over librangecoder.so).
+
+The only golden vector the reference holds for this step is the test-suite of the third-party `range_coder`
+package it vendors as other/test_range_coder.py.  Where /root/reference is mounted that file
+is run UNMODIFIED against this module (aliased as `range_coder`); its known-answer vector is restated here so
+it also runs on the GPU box."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tf_image_compression_b200 import range_coder as RC
+
+ROOT = Path(__file__).resolve().parents[1]
+REF_TEST = Path("/root/reference/other/test_range_coder.py")
+
+
+def test_known_answer_vector(tmp_path):
+    """other/test_range_coder.py:37-68: cumFreq [0,4,6,8], 17 x [0,0,0,0,1,2] -> 17 bytes; bytes 4..16 == 0x0b."""
+    path = tmp_path / "kat.bin"
+    enc = RC.RangeEncoder(str(path))
+    enc.encode([0, 0, 0, 0, 1, 2] * 17, [0, 4, 6, 8])
+    enc.close()
+    raw = path.read_bytes()
+    assert len(raw) == 17
+    assert raw[4:] == b"\x0b" * 13
+    with pytest.raises(RuntimeError):
+        enc.encode([0], [0, 4, 6, 8])  # closed
+    dec = RC.RangeDecoder(str(path))
+    assert dec.decode(6 * 17, [0, 4, 6, 8]) == [0, 0, 0, 0, 1, 2] * 17
+    dec.close()
+
+
+def test_error_conventions(tmp_path):
+    enc = RC.RangeEncoder(str(tmp_path / "e.bin"))
+    data = [0, 1, 2]
+    with pytest.raises(OverflowError):
+        enc.encode(data, [-1, 1])
+    with pytest.raises(OverflowError):
+        enc.encode(data, [0, 1, 2 ** 32])
+    for bad in ([1, 2, 3], [0, 1], [0, 8, 8, 8], [], [0], [0, 5, 3, 8]):
+        with pytest.raises(ValueError):
+            enc.encode(data, bad)
+    enc.close()
+    dec = RC.RangeDecoder(str(tmp_path / "e.bin"))
+    for bad in ([], [0]):
+        with pytest.raises(ValueError):
+            dec.decode(3, bad)
+    assert dec.decode(0, [0, 4, 6, 8]) == []
+    with pytest.raises(RuntimeError):
+        RC.RangeEncoder(str(tmp_path / "no_such_dir" / "x.bin"))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_round_trip_mixed_tables_and_dtypes(tmp_path, seed):
+    rs = np.random.RandomState(seed)
+    path = str(tmp_path / "rt.bin")
+    tables, chunks = [], []
+    for _ in range(5):
+        k = rs.randint(1, 40)
+        cum = [0] + [int(v) for v in np.cumsum(rs.randint(1, 200, size=k))]
+        n = rs.randint(0, 3000)
+        tables.append(cum)
+        chunks.append(rs.randint(0, k, size=n).astype(np.uint8))
+    enc = RC.RangeEncoder(path)
+    for cum, c in zip(tables, chunks):
+        enc.encode(c if seed % 2 else c.tolist(), cum)  # uint8 array fast path and the list path give the same stream
+    enc.close()
+    assert enc.bytes_written == os.path.getsize(path)
+    dec = RC.RangeDecoder(path)
+    for cum, c in zip(tables, chunks):
+        got = dec.decode(len(c), cum, dtype=np.uint8)
+        assert np.array_equal(got, c)
+    dec.close()
+
+
+def test_binary_symbols_reach_the_entropy(tmp_path):
+    """q = 2 (every shipped config): 1e6 symbols with p(1) = 0.1 -> within 0.5 % of the table's cross entropy."""
+    rs = np.random.RandomState(5)
+    sym = (rs.rand(1_000_000) < 0.1).astype(np.uint8)
+    prob = np.bincount(sym, minlength=2) / sym.size
+    freq = prob * 4096 + 1  # encode.py:82-91
+    cum = RC.prob_to_cum_freq(freq / freq.sum(), resolution=4096)
+    path = str(tmp_path / "b.bin")
+    enc = RC.RangeEncoder(path)
+    enc.encode(sym, cum)
+    enc.close()
+    q = np.diff(cum) / cum[-1]
+    ideal_bits = -(np.log2(q[sym.astype(int)])).sum()
+    assert os.path.getsize(path) * 8 <= ideal_bits * 1.005 + 64
+    dec = RC.RangeDecoder(path)
+    assert np.array_equal(dec.decode(sym.size, cum, dtype=np.uint8), sym)
+
+
+def test_prob_to_cum_freq_invariants():
+    rs = np.random.RandomState(190)
+    p0 = rs.dirichlet([0.1] * 50)
+    c0 = RC.prob_to_cum_freq(p0, 1024)
+    p1 = RC.cum_freq_to_prob(c0)
+    assert c0[0] == 0 and c0[-1] == 1024 and len(c0) == 51
+    assert np.all(np.diff(c0)[p0 > 0] > 0)
+    assert np.isclose(p1.sum(), 1.0)
+    assert RC.prob_to_cum_freq(p1, 1024) == c0
+    assert RC.prob_to_cum_freq([0.5, 0.25, 0.25], resolution=8) == [0, 4, 6, 8]
+    z = RC.prob_to_cum_freq([0.5, 0.0, 0.25, 0.25, 0.0, 0.0], resolution=8)
+    assert [z[0]] + [z[i + 1] for i, p in enumerate([0.5, 0.0, 0.25, 0.25, 0.0, 0.0]) if p > 0] == [0, 4, 6, 8]
+
+
+@pytest.mark.skipif(not REF_TEST.exists(), reason="/root/reference is not mounted (GPU box)")
+def test_reference_suite_passes_unmodified(tmp_path):
+    """Run the reference's own other/test_range_coder.py against this module, aliased as `range_coder`."""
+    shim = tmp_path / "range_coder"
+    shim.mkdir()
+    (shim / "__init__.py").write_text(
+        "import sys\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from tf_image_compression_b200.range_coder import RangeEncoder, RangeDecoder, prob_to_cum_freq, cum_freq_to_prob\n")
+    env = dict(os.environ, PYTHONPATH=str(tmp_path))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", str(REF_TEST)], env=env,
+                       capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -171,8 +171,9 @@ def test_quan_scale_256():
     codec.close()
 
 
-def test_postfilter_and_rmbe_match_oracle():
-    codec, enc, dec = make_codec("model_1", "fanin")
+@pytest.mark.parametrize("mode", MODES)
+def test_postfilter_and_rmbe_match_oracle(mode):
+    codec, enc, dec = make_codec("model_1", "fanin", compute=mode)
     pp = O.init_params(O.POSTFILTERS["rmbe"], 3, 77, "fanin")
     pm, ps = np.array([110.0, 108.0, 99.0], np.float32), np.array([55.0, 57.0, 60.0], np.float32)
     codec.set_postfilter(pp, pm, ps)
@@ -199,8 +200,9 @@ def test_postfilter_and_rmbe_match_oracle():
     codec.close()
 
 
-def test_device_buffers_chunking_and_determinism():
-    codec, enc, dec = make_codec("model_0", "fanin")
+@pytest.mark.parametrize("mode", MODES)
+def test_device_buffers_chunking_and_determinism(mode):
+    codec, enc, dec = make_codec("model_0", "fanin", compute=mode)
     patches = patches_from_images(2, 384, 512, 128, seed=50)  # 24 patches
     base = codec.encode_patches(patches)
     d_in = torch.from_numpy(patches).cuda()
@@ -246,7 +248,8 @@ def test_reference_module_surface_and_errors():
     codec.close()
 
 
-def test_golden_fixture_cfg1():
+@pytest.mark.parametrize("mode", MODES)
+def test_golden_fixture_cfg1(mode):
     """BASELINE config 1 (768x512 image, model_0, 128x128 patches) against the committed fixture
     (tests/golden/make_golden.py)."""
     from pathlib import Path
@@ -257,7 +260,7 @@ def test_golden_fixture_cfg1():
     dec = O.condition_decoder("model_0", dec, 2)
     chk = [float(sum(np.float64(v).sum() for v in enc.values())), float(sum(np.float64(v).sum() for v in dec.values()))]
     np.testing.assert_allclose(chk, z["weight_checksum"], rtol=0, atol=1e-9)
-    codec = T.Codec("model_0", quan_scale=2, mean=z["mean"], std=z["std"], enc_params=enc, dec_params=dec)
+    codec = T.Codec("model_0", quan_scale=2, mean=z["mean"], std=z["std"], enc_params=enc, dec_params=dec, compute=mode)
     sym = codec.encode_images(z["image"][None], 128)[0]
     assert sym.shape == (24, 8, 8, 64)
     packed = np.packbits(sym.reshape(-1))
@@ -268,10 +271,11 @@ def test_golden_fixture_cfg1():
     codec.close()
 
 
-def test_full_size_properties_cfg2_shard():
+@pytest.mark.parametrize("mode", MODES)
+def test_full_size_properties_cfg2_shard(mode):
     """BASELINE config 2 at one GPU's 8-image share (8 x 2048x1536, 1 536 patches): size-independent
     properties — determinism, batch == per-image, histogram == symbol count, decode idempotence."""
-    codec, enc, dec = make_codec("model_0", "fanin")
+    codec, enc, dec = make_codec("model_0", "fanin", compute=mode)
     rs = np.random.RandomState(1234)
     imgs = rs.randint(0, 256, size=(8, 1536, 2048, 3), dtype=np.uint8)
     d_imgs = torch.from_numpy(imgs).cuda()
@@ -291,4 +295,86 @@ def test_full_size_properties_cfg2_shard():
     # spot-check one patch of one image against the oracle
     p = imgs[3, 128:256, 256:384][None].astype(np.float32)
     assert (O.encoder(p, "model_0", enc, MEAN, STD, 2)[0] != sym[3, 1 * 16 + 2].cpu().numpy()).sum() <= 1
+    codec.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cfg4_distribution_table_and_bitstreams(mode, tmp_path):
+    """BASELINE config 4: base_model/reduced_btn_32 (bottleneck_channel from config), dataset-wide symbol table
+    (fused histogram == np.histogram of the oracle's symbols, get_encoded_distribution.py:113-134), range-coded
+    files byte-identical to coding the oracle's symbols, and the decode side of the round trip."""
+    from tf_image_compression_b200 import entry, range_coder
+    variant = "base_model/reduced_btn_32"
+    codec, enc, dec = make_codec(variant, "fanin", compute=mode)
+    cfg = dict(entry.DEFAULT_CONFIG, patch_size=128, bottleneck_channel=32)
+    images = [O.synthetic_image(256, 384, 70 + i) for i in range(3)] + [O.synthetic_image(200, 300, 90)]  # ragged size too
+    names = [f"/data/x/img_{i}.png" for i in range(len(images))]
+    patches = np.stack([p for im in images for p in O.crop_image_input_patches(im, 128)])
+    prob = entry.get_distribution(codec, patches)
+    counts = codec.hist_read()
+    ref_sym = O.encoder(patches.astype(np.float32), variant, enc, MEAN, STD, 2).astype(np.uint8)
+    gpu_sym = codec.encode_patches(patches)
+    mism = int((gpu_sym != ref_sym).sum())
+    assert mism <= max(1, int(1e-5 * ref_sym.size)), mism  # round-half boundary only (north_star: <= 1e-5)
+    # the fused histogram is exactly np.histogram of the emitted symbols (get_encoded_distribution.py:121-126)
+    assert np.array_equal(counts.astype(np.int64), np.histogram(gpu_sym, bins=[0, 1, 2])[0])
+    assert np.allclose(prob, counts / counts.sum())
+    out = entry.compress(codec, images, names, cfg, prob, str(tmp_path / "enc"))
+    cum = entry.cum_freq_table(prob, 4096)
+    k = 0
+    for (path, nbytes), im in zip(out, images):
+        npatch = len(O.crop_image_input_patches(im, 128))
+        stem, eshape, n, h, w = entry.parse_encoded_name(os.path.basename(path), cfg)
+        assert eshape == (32, 32, 32) and n == npatch * 32 * 32 * 32 and (h, w) == im.shape[:2]
+        # bitstreams are byte-identical wherever the symbols are identical: code the oracle's symbols with the same table
+        if np.array_equal(gpu_sym[k:k + npatch], ref_sym[k:k + npatch]):
+            ref_path = tmp_path / "ref.bin"
+            e = range_coder.RangeEncoder(str(ref_path))
+            e.encode(ref_sym[k:k + npatch].reshape(-1), cum)
+            e.close()
+            assert ref_path.read_bytes() == open(path, "rb").read()
+        assert nbytes == os.path.getsize(path)
+        k += npatch
+    ref_sym = gpu_sym  # the decode side is checked on the symbols that were actually coded
+    rec = entry.uncompress(codec, str(tmp_path / "enc"), cfg, prob)
+    assert sorted(rec) == [f"img_{i}" for i in range(len(images))]
+    k = 0
+    for i, im in enumerate(images):
+        npatch = len(O.crop_image_input_patches(im, 128))
+        want = O.around_u8(O.concat_patches(list(O.decoder(ref_sym[k:k + npatch], variant, dec, MEAN, STD, 2)), im.shape[0], im.shape[1], 128))
+        d = np.abs(rec[f"img_{i}"].astype(int) - want.astype(int))
+        assert rec[f"img_{i}"].shape == im.shape and d.max() <= 1 and (d != 0).mean() < 1e-4
+        k += npatch
+    assert entry.bpp([b for _, b in out], images) > 0 and np.isfinite(entry.psnr(images, [rec[f"img_{i}"] for i in range(len(images))]))
+    codec.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cfg5_model1_decode_and_rmbe(mode):
+    """BASELINE config 5: model_1 (P = 256) decode -> stitch -> rmbe post-filter -> round, call order of
+    submit/2/decoder.py:183-198; oracle parity on a 512x768 image, size-independent properties at 2048x1536."""
+    codec, enc, dec = make_codec("model_1", "fanin", compute=mode)
+    pp = O.init_params(O.POSTFILTERS["rmbe"], 3, 77, "fanin")
+    pm, ps = np.array([110.0, 108.0, 99.0], np.float32), np.array([55.0, 57.0, 60.0], np.float32)
+    codec.set_postfilter(pp, pm, ps)
+    rs = np.random.RandomState(8)
+    sym = rs.randint(0, 2, size=(1, 6, 16, 16, 64)).astype(np.uint8)  # 512x768 at P = 256: 2 x 3 patches
+    got = codec.decode_images(sym, 512, 768, 256, out_dtype=np.float32)
+    want = O.concat_patches(list(O.decoder(sym[0], "model_1", dec, MEAN, STD, 2)), 512, 768, 256)
+    assert float(np.abs(got[0] - want).max()) <= 1e-3
+    codec.postfilter_images(got)
+    want = O.rmbe(want.astype(np.float32), lambda t: O.postfilter(t, "rmbe", pp, pm, ps))
+    assert float(np.abs(got[0] - want).max()) <= 3e-3  # decoder + two chained filter passes
+    out8 = codec.round_u8(got)
+    assert out8.dtype == np.uint8 and np.abs(out8[0].astype(int) - O.around_u8(want).astype(int)).max() <= 1
+    # full size: 2048x1536 -> 48 patches of 256, 356 filter tiles per image; deterministic, borders untouched
+    big = torch.from_numpy(rs.randint(0, 2, size=(2, 48, 16, 16, 64)).astype(np.uint8)).cuda()
+    img = codec.decode_images(big, 1536, 2048, 256, out_dtype=np.float32)
+    before = img.clone()
+    codec.postfilter_images(img)
+    again = before.clone()
+    codec.postfilter_images(again)
+    assert torch.equal(img, again)
+    assert torch.equal(img[:, :64, :64], before[:, :64, :64]) and not torch.equal(img[:, 64:192, 64:192], before[:, 64:192, 64:192])
+    assert float(img.min()) >= 0.0 and float(img.max()) <= 255.0
     codec.close()

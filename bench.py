@@ -7,7 +7,7 @@ Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JS
              GPU (weak scaling: every rank encodes + decodes its own 64 images; no data-path collective)
   value    : device-resident throughput (inputs already in HBM, CUDA events, max over ranks)
   e2e      : same metric through the public API with pinned HOST buffers (H2D + kernels + D2H)
-  roofline : dominant kernel, algorithmic FLOPs / CUDA-event time vs MEASURED_PEAKS.json
+  roofline : dominant kernel, algorithmic bytes (or FLOPs) per launch / CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline : the CPU oracle (torch-CPU fp32 restatement; TensorFlow is not installable) on a
              bounded sample of the same workload, timed on this box's host cores (rank 0, N=1 only)
 `--impl reference` times that CPU restatement alone (rank 0) with all host threads.
@@ -190,7 +190,7 @@ def run_b200(args):
     codec = T.Codec(VARIANT, quan_scale=2, mean=MEAN, std=STD, device=local, compute="fp32", seed=1234)
     compute = args.compute
     if compute == "auto":
-        compute = os.environ.get("TIC_DEFAULT_COMPUTE", "tensor")  # 3xTF32 tcgen05 path (parity-green)
+        compute = os.environ.get("TIC_DEFAULT_COMPUTE", "tensor")  # fp16-pair tcgen05 path (parity-green)
     codec.set_compute(compute)
     codec.use_torch_stream()
     if args.chunk > 0:
@@ -260,38 +260,58 @@ def run_b200(args):
     d2h = host_sym.numel() + host_rec.numel()
 
     # ---- per-layer times (separate profiled pass, not part of the timed region) -------------------
+    # Every layer launch is bracketed by CUDA events on the codec's stream (tic_profile_*); the dominant
+    # kernel's roofline is algorithmic work per launch / its average launch duration.
+    PASSES = 3
     codec.profile(True)
-    for _ in range(3):
+    for _ in range(PASSES):
         step_device()
     torch.cuda.synchronize()
     pk = peaks()
     rows = []
+    npatch = B * gh * gw
     for graph, layers in (("encoder", codec.enc_layers), ("decoder", codec.dec_layers)):
         hh = P if graph == "encoder" else hb
+        first, last = layers[0], layers[-1]
         for (l, tot_ms, n_launch) in codec.layer_times(graph):
+            hin = hh
             if l.kind == "c":
                 hh = -(-hh // l.stride)
                 macs = hh * hh * 9 * l.cin * l.cout
             else:
                 macs = hh * hh * 9 * l.cin * l.cout
                 hh *= 2
-            flops_per_launch = 2.0 * macs * B * gh * gw / max(1, n_launch // 3)
-            rows.append(dict(graph=graph, scope=l.scope, ms=tot_ms / max(1, n_launch), launches=n_launch,
-                             flops=flops_per_launch))
+            # algorithmic bytes of this layer per patch: its input and output tensors once (activations are
+            # 4 B per element: fp16 pair planes or fp32; the u8 image / symbols / u8 reconstruction are 1 B) + weights
+            in_b = hin * hin * l.cin * (1 if l is first else 4)
+            out_b = hh * hh * l.cout * (1 if l is last else 4)
+            rows.append(dict(graph=graph, scope=l.scope, ms_step=tot_ms / PASSES, launches=max(1, n_launch // PASSES),
+                             flops_step=2.0 * macs * npatch, bytes_step=float(in_b + out_b) * npatch + 9.0 * l.cin * l.cout * 4))
     codec.profile(False)
-    step_ms = sum(r["ms"] * (r["launches"] // 3) for r in rows)
-    top = max(rows, key=lambda r: r["ms"] * r["launches"])
-    achieved = top["flops"] / (top["ms"] * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": None,
-                "kernel": f"{top['graph']}/{top['scope']} ({compute})", "peak_source": f"bf16 sustained, {pk['source']}",
-                "kernel_share_of_step": top["ms"] * (top["launches"] // 3) / max(step_ms, 1e-9),
-                "whole_step_algorithmic_tflops": world * sum(V.model_flops_per_pixel(VARIANT, P)) * pixels * args.steps
-                / (ms_max * 1e-3) / 1e12}
+    step_ms = sum(r["ms_step"] for r in rows)
+    top = max(rows, key=lambda r: r["ms_step"])
+    ridge = pk["bf16_sustained"] * 1e12 / (pk["hbm"] * 1e9)
+    top_launch_s = top["ms_step"] / top["launches"] * 1e-3
+    if top["flops_step"] / top["bytes_step"] >= ridge:
+        achieved = top["flops_step"] / top["launches"] / top_launch_s / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["bf16_sustained"], "peak_source": f"bf16 sustained, {pk['source']}"}
+    else:
+        achieved = top["bytes_step"] / top["launches"] / top_launch_s / 1e9
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                    "peak_source": f"copy bandwidth, {pk['source']}"}
+    roofline.update({
+        "traffic": None, "kernel": f"{top['graph']}/{top['scope']} ({compute})",
+        "kernel_ms_per_launch": top_launch_s * 1e3, "kernel_share_of_step": top["ms_step"] / max(step_ms, 1e-9),
+        "kernel_algorithmic_flop_per_byte": top["flops_step"] / top["bytes_step"], "ridge_flop_per_byte": ridge,
+        "whole_step_algorithmic_tflops": world * sum(V.model_flops_per_pixel(VARIANT, P)) * pixels * args.steps / (ms_max * 1e-3) / 1e12,
+        "whole_step_layer_bytes_gbs": world * sum(r["bytes_step"] for r in rows) * args.steps / (ms_max * 1e-3) / 1e9,
+    })
     if args.layers and rank == 0:
         for r in rows:
-            print(f"  {r['graph']:8s} {r['scope']:22s} {r['ms']:8.3f} ms/launch  {r['flops'] / (r['ms'] * 1e-3) / 1e12:8.2f} TFLOP/s",
-                  file=sys.stderr)
+            t = r["ms_step"] * 1e-3
+            print(f"  {r['graph']:8s} {r['scope']:22s} {r['ms_step']:8.3f} ms/step {r['launches']:3d} launches  "
+                  f"{r['flops_step'] / t / 1e12:8.2f} TFLOP/s {r['bytes_step'] / t / 1e9:8.1f} GB/s", file=sys.stderr)
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------
     cpu = None
@@ -305,7 +325,7 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if compute == "fp32" else ("3xtf32" if compute in ("tensor", "3xtf32") else "tf32"),
+            "dtype": {"fp32": "f32", "tensor": "f16x3", "f16x3": "f16x3", "3xtf32": "3xtf32", "tf32": "tf32"}.get(compute, compute),
             "data": "synthetic",
             "config": {"workload": f"{VARIANT} encode+decode of {B} synthetic 2048x1536 RGB images per GPU in {P}x{P} "
                                    f"patches ({B * gh * gw} patches, BASELINE config 2), random-init weights",

@@ -60,7 +60,9 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;                                        // kF16Stages stages
   uint8_t* s_w = smem + kF16Stages * kF16StageBytes;          // 2 * npad * 64 B
-  F16SmemBars* bars = reinterpret_cast<F16SmemBars*>(s_w + 2 * 64 * 64);
+  uint8_t* s_stage = s_w + 2 * 64 * 64;                       // 8 x 4 KB epilogue stages
+  F16SmemBars* bars = reinterpret_cast<F16SmemBars*>(s_stage + kU16StageBytes);
+  const bool staged = u16_staged_ok(a, U16_S1, p.nbuf, p.npad);
   __shared__ unsigned s_hist[256];
   __shared__ __align__(16) float s_bias[128];
   __shared__ float s_lut[3 * 256];
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
-      ptx::mbar_init(&bars->acc_empty[i], 8);
+      ptx::mbar_init(&bars->acc_empty[i], staged ? 4 : 8);
     }
     ptx::fence_barrier_init();
   }
@@ -234,6 +236,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
     int h_ones = 0, h_valid = 0;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if (staged && (int)(it & 1u) != half) continue;  // staged: a warp group owns every other tile
       const uint32_t b = it & bmask;
       ptx::mbar_wait(&bars->acc_full[b], (it >> nbshift) & 1);
       ptx::tc_fence_after();
@@ -243,8 +246,12 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
       const int ty = (int)(tt % p.tiles_y);
       const int n = (int)(tt / p.tiles_y) * p.bn + nb;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
-      u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * p.bh + hh, tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
-                                h_valid);
+      if (staged)
+        u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * p.bh + hh, tx * 8 + xx, n < p.n, s_bias,
+                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0);
+      else
+        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * p.bh + hh, tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
+                                  h_valid);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
@@ -313,7 +320,9 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;                                  // kW2Stages stages of kW2Stage bytes
   uint8_t* s_w = smem + kW2Stages * 10240;              // 192 * npad bytes
-  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_w + 192 * 64);
+  uint8_t* s_stage = s_w + 192 * 64;                    // 8 x 4 KB epilogue stages
+  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_stage + kU16StageBytes);
+  const bool staged = u16_staged_ok(a, U16_S1, p.nbuf, p.npad);
   __shared__ unsigned s_hist[256];
   __shared__ __align__(16) float s_bias[128];
   __shared__ uint32_t s_plut[3 * 256];  // u8 -> (hi | lo' << 16) of the normalised value: no split in the hot loop
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
-      ptx::mbar_init(&bars->acc_empty[i], 8);
+      ptx::mbar_init(&bars->acc_empty[i], staged ? 4 : 8);
     }
     ptx::fence_barrier_init();
   }
@@ -517,6 +526,7 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
     int h_ones = 0, h_valid = 0;
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if (staged && (int)(it & 1u) != half) continue;  // staged: a warp group owns every other tile
       const uint32_t b = it & bmask;
       ptx::mbar_wait(&bars->acc_full[b], (it >> nbshift) & 1);
       ptx::tc_fence_after();
@@ -526,7 +536,11 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
       const int ty = (int)(tt % p.tiles_y);
       const int n = (int)(tt / p.tiles_y);
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
-      u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * 16 + hh, tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
+      if (staged)
+        u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * 16 + hh, tx * 8 + xx, true, s_bias,
+                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0);
+      else
+        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * 16 + hh, tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
@@ -605,8 +619,8 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
     if (cudaGetLastError() != cudaSuccess) return fail("first-layer weight image kernel failed", -2);
   }
   p.wimg = fw->img;
-  const size_t smem = kF16Stages * kF16StageBytes + 2 * 64 * 64 + sizeof(F16SmemBars) + 1024;
-  const size_t smem_w2 = kW2Stages * 10240 + 192 * 64 + sizeof(W2SmemBars) + 1024;
+  const size_t smem = kF16Stages * kF16StageBytes + 2 * 64 * 64 + kU16StageBytes + sizeof(F16SmemBars) + 1024;
+  const size_t smem_w2 = kW2Stages * 10240 + 192 * 64 + kU16StageBytes + sizeof(W2SmemBars) + 1024;
   const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
   static bool configured = false;
   if (!configured) {

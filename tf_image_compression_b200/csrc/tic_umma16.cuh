@@ -48,7 +48,10 @@ namespace tic {
 // U16_DECONV_PH ("phase-stacked", cout <= 32): N = (phase, channel); the taps that read the same input pixel
 // ("view": a / a-1 x b / b-1) are stacked along N with zero rows for the phases a view does not reach:
 // 4 MMA pairs per K step instead of 9, and it is what makes the 3-channel last layer a tensor-core layer.
-enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2, U16_DECONV_PH = 3 };
+// U16_DECONV_RGB: phase-stacked with cpad = 4 (the 3-channel last layer); its own instantiation so that its
+// epilogue (denormalise, clip, round, scatter into the stitched image) is not compiled next to the others.
+enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2, U16_DECONV_PH = 3, U16_DECONV_RGB = 4 };
+__host__ __device__ constexpr bool u16_is_ph(int mode) { return mode == U16_DECONV_PH || mode == U16_DECONV_RGB; }
 
 constexpr int kU16Threads = 384;
 constexpr int kU16MaxSlots = 6;
@@ -83,6 +86,7 @@ struct U16Params {
   uint32_t w_bytes;      // KB * 9 * tap_bytes
   const uint8_t* wimg;
   int pair;              // 1: CTA-pair kernel (cta_group::2, M = 256)
+  int staged;            // 1: coalesced epilogue through a per-warp shared-memory stage (u16_epilogue_tile_staged)
   uint32_t wA_bytes;     // pair: per-CTA bytes of its half of the stacked weight tiles (all taps, K-blocks)
   uint32_t wB_bytes;     // pair: per-CTA bytes of its half of W_hi for the A_lo' x W_hi product
   long long in_lo_off;   // elements between the hi and lo' planes of the input (unused by the kernel: second tensor map)
@@ -247,10 +251,10 @@ __device__ __forceinline__ uint64_t u16_desc(uint32_t lo32, uint32_t hi32) {
 template <int MODE>
 __device__ __forceinline__ void u16_load_chunk(float (&v)[16], const uint32_t tbuf, const int NPAD, const int nsplit,
                                                const int ph, const int c, const int cpad) {
-  constexpr bool kDeconv = MODE == U16_DECONV || MODE == U16_DECONV_PH;
+  constexpr bool kDeconv = MODE == U16_DECONV || u16_is_ph(MODE);
   if (kDeconv || nsplit == 1) {
     float u[16];
-    const uint32_t t0 = tbuf + (MODE == U16_DECONV_PH ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
+    const uint32_t t0 = tbuf + (u16_is_ph(MODE) ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
     ptx::tmem_ld16_nowait(t0 + NPAD, u);
     ptx::tmem_ld16_nowait(t0, v);
     ptx::tmem_ld_wait();
@@ -295,11 +299,11 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
                                                   const uint32_t tbuf, const int n, const int yt, const int xt, const bool valid,
                                                   const int half, const float* s_bias, unsigned* s_hist, int& h_ones,
                                                   int& h_valid, const int cpad = 0) {
-  constexpr bool kDeconv = MODE == U16_DECONV || MODE == U16_DECONV_PH;
+  constexpr bool kDeconv = MODE == U16_DECONV || u16_is_ph(MODE);
 #ifdef TIC_DEBUG_SKIP_EPILOGUE  // measurement aid: time the kernels without their epilogue work
   return;
 #endif
-  if (MODE == U16_DECONV_PH && cpad == 4) {
+  if (MODE == U16_DECONV_RGB) {
     // 3-channel last layer: the 16 columns are (phase, channel) of the 2x2 output pixels of this input pixel;
     // the two warps of a lane quadrant take the even / the odd output row
     float v[16], u[16];
@@ -346,7 +350,7 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
     return;
   }
   const int phases = kDeconv ? 4 : 1;
-  const int cend = MODE == U16_DECONV_PH ? cpad : NPAD;
+  const int cend = u16_is_ph(MODE) ? cpad : NPAD;
   if (a.out_mode == IO_ACT16 && (a.cout & 15) == 0) {
     // ---- fast path: pair-plane output, every chunk holds 16 real channels --------------------------------
     const float floor_v = a.act ? 0.0f : -INFINITY;
@@ -397,7 +401,7 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
       const int ph = u / nch;
       c = (u - ph * nch) << 4;
       poff = kDeconv ? ((ph >> 1) * a.wout + (ph & 1)) * a.cout : 0;
-      return tbuf + (MODE == U16_DECONV_PH ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
+      return tbuf + (u16_is_ph(MODE) ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
     };
     if (kDeconv || nsplit == 1) {
       for (int u = half; u < U; u += 4) {
@@ -506,20 +510,161 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
   }
 }
 
+// ---- staged epilogue: coalesced pair-plane stores ---------------------------------------------------------
+// A lane's pixel row is `cend * 2` bytes per plane, so direct stores are 16 bytes per lane at a stride of a
+// row: 32 transactions per instruction (measured: the deconv epilogue was store-transaction-bound at ~5.6 k
+// cycles per tile).  Here a warp owns ALL channels of its 32 pixels for every other tile (its own TMEM
+// buffer), stages one plane of them in 4 KB of shared memory (16-byte chunks XOR-swizzled against bank
+// conflicts) and writes it back with consecutive lanes on consecutive 16-byte chunks: a warp's 8-pixel rows
+// are contiguous in the NHWC tensor, so every store instruction covers whole 512-byte runs.
+constexpr uint32_t kU16StagePerWarp = 4096;
+constexpr uint32_t kU16StageBytes = 8 * kU16StagePerWarp;
+
+__host__ __device__ inline bool u16_staged_ok(const LayerArgs& a, int mode, int nbuf, int cend) {
+  if (nbuf < 2 || a.out_mode != IO_ACT16 || (a.cout & 15) != 0) return false;
+  if (mode == U16_DECONV) return false;                       // tap-based 64-channel deconv: one TMEM buffer
+  // 64-channel layers sit on 8x8 / 16x16 maps at the HBM roofline already and need the 32 KB for operand slots
+  if (!(cend == 16 || cend == 32)) return false;
+  if (cend != a.cout) return false;                           // output-channel slices: the row is not owned by one launch
+  return true;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// CEND = channels of this launch per pixel (16 | 32 | 64): all stage index arithmetic is compile-time.
+template <int MODE, int CEND>
+__device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
+                                                           const uint32_t tbuf, const int n, const int yt, const int xt,
+                                                           const bool valid, const float* s_bias, const uint32_t stage,
+                                                           const int lane, const int cpad) {
+  constexpr bool kPh = u16_is_ph(MODE);
+  constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane: 2 | 4 | 8
+  constexpr int MSH = M == 2 ? 1 : (M == 4 ? 2 : 3);
+  constexpr int FSH = 3 - MSH;                       // swizzle: chunk ^= (pixel >> FSH) & (M - 1)
+  constexpr int NCI = CEND / 16;
+  constexpr int NPX = kPh ? 2 : 1;
+  constexpr int NPIX = kPh ? 64 : 32;                // output pixels per warp and pass
+  const float floor_v = a.act ? 0.0f : -INFINITY;
+  const long long pix0 = ((long long)n * a.hout + (kPh ? 2 * yt : yt)) * a.wout + (kPh ? 2 * xt : xt);
+  // offset of this lane's (first) output pixel inside a plane in 16-byte units; -1 = invalid pixel (odd tail patch)
+  const int my_off16 = valid ? (int)(((pix0 * a.cout + oc0) * 2) >> 4) : -1;
+  const int row16 = (a.cout * 2) >> 4;               // one pixel row in 16-byte units
+  uint4* const ohi = reinterpret_cast<uint4*>(a.out);
+  uint4* const olo = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.out) + a.out_lo_off);
+  const __half* const rbase = a.res ? reinterpret_cast<const __half*>(a.res) + pix0 * a.cout + oc0 : nullptr;
+#pragma unroll 1
+  for (int py = 0; py < (kPh ? 2 : 1); ++py) {
+    uint32_t lp[NPX][NCI][8];                        // lo' words kept while the hi plane goes through the stage
+#pragma unroll
+    for (int px = 0; px < NPX; ++px) {
+      const int ph = py * 2 + px;
+      const int spix = kPh ? ((lane >> 3) * 16 + 2 * (lane & 7) + px) : lane;   // pixel slot in the stage
+      const uint32_t sp = stage + (uint32_t)spix * (M * 16);
+      const int sw = (spix >> FSH) & (M - 1);
+#pragma unroll
+      for (int ci = 0; ci < NCI; ++ci) {
+        const int c = ci * 16;
+        float v[16];
+        u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = bp[i];
+          v[4 * i] = fmaxf(__fadd_rn(v[4 * i], b.x), floor_v);
+          v[4 * i + 1] = fmaxf(__fadd_rn(v[4 * i + 1], b.y), floor_v);
+          v[4 * i + 2] = fmaxf(__fadd_rn(v[4 * i + 2], b.z), floor_v);
+          v[4 * i + 3] = fmaxf(__fadd_rn(v[4 * i + 3], b.w), floor_v);
+        }
+        if (!kPh && rbase && valid) {
+          const uint4* rh = reinterpret_cast<const uint4*>(rbase + c);
+          const uint4* rl = reinterpret_cast<const uint4*>(rbase + a.res_lo_off + c);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 qh = __ldg(rh + j), ql = __ldg(rl + j);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&qh);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+              v[8 * j + 2 * e] = __fadd_rn(__fmaf_rn(lf.x, 1.0f / 2048.0f, hf.x), v[8 * j + 2 * e]);
+              v[8 * j + 2 * e + 1] = __fadd_rn(__fmaf_rn(lf.y, 1.0f / 2048.0f, hf.y), v[8 * j + 2 * e + 1]);
+            }
+          }
+        }
+        uint32_t hp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[px][ci][i]);
+        sts128(sp + (uint32_t)(((2 * ci) ^ sw) << 4), hp[0], hp[1], hp[2], hp[3]);
+        sts128(sp + (uint32_t)(((2 * ci + 1) ^ sw) << 4), hp[4], hp[5], hp[6], hp[7]);
+      }
+    }
+    // ---- write back one plane: chunk q of the stage -> its pixel's row in global memory ------------------
+    const int row_off16 = kPh ? py * a.wout * row16 : 0;
+    auto flush = [&](uint4* plane) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NPIX * M / 32; ++j) {
+        const int q = lane + 32 * j;
+        const int sp_ix = q >> MSH, cq = q & (M - 1);
+        const int owner = kPh ? ((sp_ix >> 4) * 8 + ((sp_ix & 15) >> 1)) : sp_ix;
+        const int base = __shfl_sync(0xffffffffu, my_off16, owner);
+        const int sw = (sp_ix >> FSH) & (M - 1);
+        const uint4 val = lds128(stage + (uint32_t)((sp_ix * M + (cq ^ sw)) << 4));
+        if (base >= 0) plane[(long long)base + row_off16 + (kPh ? (sp_ix & 1) * row16 : 0) + cq] = val;
+      }
+      __syncwarp();
+    };
+    flush(ohi);
+#pragma unroll
+    for (int px = 0; px < NPX; ++px) {
+      const int spix = kPh ? ((lane >> 3) * 16 + 2 * (lane & 7) + px) : lane;
+      const uint32_t sp = stage + (uint32_t)spix * (M * 16);
+      const int sw = (spix >> FSH) & (M - 1);
+#pragma unroll
+      for (int ci = 0; ci < NCI; ++ci) {
+        sts128(sp + (uint32_t)(((2 * ci) ^ sw) << 4), lp[px][ci][0], lp[px][ci][1], lp[px][ci][2], lp[px][ci][3]);
+        sts128(sp + (uint32_t)(((2 * ci + 1) ^ sw) << 4), lp[px][ci][4], lp[px][ci][5], lp[px][ci][6], lp[px][ci][7]);
+      }
+    }
+    flush(olo);
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void u16_epilogue_tile_staged(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
+                                                         const uint32_t tbuf, const int n, const int yt, const int xt,
+                                                         const bool valid, const float* s_bias, uint8_t* stage, const int lane,
+                                                         const int cpad) {
+  if (MODE == U16_DECONV_RGB) return;
+  const int cend = u16_is_ph(MODE) ? cpad : NPAD;
+  const uint32_t st = ptx::smem_u32(stage);
+  if (cend == 32)
+    u16_epilogue_tile_staged_t<MODE, 32>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad);
+  else if (cend == 16)
+    u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad);
+}
+
 template <int MODE, bool PAIR = false>
 __device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
                                                 uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
                                                 uint32_t tapw, int ksteps, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
                                                 bool fresh_kb) {
 #pragma unroll
-  for (int tap = 0; tap < (MODE == U16_DECONV_PH ? 4 : 9); ++tap) {  // PH: tap = view
+  for (int tap = 0; tap < (u16_is_ph(MODE) ? 4 : 9); ++tap) {  // PH: tap = view
     const uint32_t ad = abase + (p.a_off[tap] >> 4);
     const uint32_t bd = wbase + (uint32_t)tap * tapw;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       if (ks < ksteps) {
         uint32_t d, accumulate;
-        if (MODE == U16_DECONV_PH) {
+        if (u16_is_ph(MODE)) {
           d = dplane;
           accumulate = (fresh_kb && tap == 0 && ks == 0) ? 0u : 1u;
         } else if (MODE == U16_DECONV) {
@@ -554,7 +699,8 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_w = smem;                                             // resident weights
   uint8_t* s_a = smem + ((p.w_bytes + 1023u) & ~1023u);            // S plane slots
-  U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_a + (size_t)p.S * p.slot_bytes);
+  uint8_t* s_stage = s_a + (size_t)p.S * p.slot_bytes;             // 8 x 4 KB epilogue stages (if p.staged)
+  U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_stage + (p.staged ? kU16StageBytes : 0u));
   __shared__ unsigned s_hist[256];
   __shared__ __align__(16) float s_bias[128];
 
@@ -569,7 +715,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
-      ptx::mbar_init(&bars->acc_empty[i], 8);
+      ptx::mbar_init(&bars->acc_empty[i], p.staged ? 4 : 8);
     }
     ptx::fence_barrier_init();
   }
@@ -647,7 +793,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
-            const uint32_t wbase = (ptx::smem_u32(s_w + (size_t)kb * (MODE == U16_DECONV_PH ? 4 : 9) * p.tap_bytes) >> 4) | (1u << 16);
+            const uint32_t wbase = (ptx::smem_u32(s_w + (size_t)kb * (u16_is_ph(MODE) ? 4 : 9) * p.tap_bytes) >> 4) | (1u << 16);
             uint32_t sp = 0, fresh_left = (plane == 0 && kb == 0) ? (uint32_t)p.nsplit : 0u;
             u16_issue_plane<MODE>(p, abase, wbase, dbase + (plane ? (uint32_t)NPAD : 0u), pairw, plane ? idesc_lo : idesc_st,
                                   a_hi32, w_hi32, tapw, ksteps, smask, sp, fresh_left, plane == 0 && kb == 0);
@@ -670,6 +816,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     int h_ones = 0, h_valid = 0;
     uint32_t ti = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
+      if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
       const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
       const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
@@ -682,7 +829,11 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
-      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
+      if (p.staged)
+        u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
+                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad);
+      else
+        u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
@@ -729,7 +880,8 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint8_t* s_wA = smem;                                            // this CTA's half of the stacked weight tiles
   uint8_t* s_wB = smem + ((p.wA_bytes + 1023u) & ~1023u);          // this CTA's half of W_hi
   uint8_t* s_a = s_wB + ((p.wB_bytes + 1023u) & ~1023u);           // S plane slots
-  U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_a + (size_t)p.S * p.slot_bytes);
+  uint8_t* s_stage = s_a + (size_t)p.S * p.slot_bytes;             // 8 x 4 KB epilogue stages (if p.staged)
+  U16SmemBars* bars = reinterpret_cast<U16SmemBars*>(s_stage + (p.staged ? kU16StageBytes : 0u));
   __shared__ unsigned s_hist[256];
   __shared__ __align__(16) float s_bias[128];
 
@@ -746,7 +898,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
-      ptx::mbar_init(&bars->acc_empty[i], 16);        // 8 epilogue warps of each CTA (leader's copy is the live one)
+      ptx::mbar_init(&bars->acc_empty[i], p.staged ? 8 : 16);  // epilogue warps of both CTAs (leader's copy is the live one)
     }
     ptx::fence_barrier_init();
   }
@@ -816,7 +968,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const uint32_t idesc_lo = ptx::make_idesc_f16(256, NPAD);
       const uint32_t a_hi32 = (p.sbo >> 4) | (1u << 14) | (p.a_layout << 29);
       const uint32_t w_hi32 = (p.w_sbo >> 4) | (1u << 14) | (p.w_layout << 29);
-      constexpr uint32_t T = MODE == U16_DECONV_PH ? 4u : 9u;
+      constexpr uint32_t T = u16_is_ph(MODE) ? 4u : 9u;
       const uint32_t tapA = (uint32_t)NPAD * (uint32_t)p.kc * 2u, tapB = tapA >> 1;
       const uint32_t pairw = 2u * (uint32_t)NPAD, smask = (uint32_t)p.nsplit - 1u;
       const int ksteps = p.ksteps;
@@ -861,6 +1013,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     int h_ones = 0, h_valid = 0;
     uint32_t ti = 0;
     for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
+      if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
       const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
       const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
@@ -873,7 +1026,11 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
-      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
+      if (p.staged)
+        u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
+                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad);
+      else
+        u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&bars->acc_empty[b]);
@@ -1062,8 +1219,9 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
     p.acc_cols = (uint32_t)(p.nsplit * accw);
   }
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
+  p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad) ? 1 : 0;
   const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
-  const size_t wres = (p.w_bytes + 1023u) & ~1023u;
+  const size_t wres = ((p.w_bytes + 1023u) & ~1023u) + (p.staged ? kU16StageBytes : 0u);
   if (wres + 2 * (size_t)p.slot_bytes > budget) return false;
   p.S = (int)std::min<size_t>(kU16MaxSlots, (budget - wres) / p.slot_bytes);
   out->cs = cs;
@@ -1159,6 +1317,8 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
         e = u16_launch_pair_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
       else if (p.mode == U16_S2)
         e = u16_launch_pair_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else if (p.mode == U16_DECONV_PH && p.cpad == 4)
+        e = u16_launch_pair_t<U16_DECONV_RGB>(stream, tm[0], tm[1], p, a, grid, pl.smem);
       else if (p.mode == U16_DECONV_PH)
         e = u16_launch_pair_t<U16_DECONV_PH>(stream, tm[0], tm[1], p, a, grid, pl.smem);
       else
@@ -1169,6 +1329,8 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
         e = u16_launch_t<U16_S1>(stream, tm[0], tm[1], p, a, grid, pl.smem);
       else if (p.mode == U16_S2)
         e = u16_launch_t<U16_S2>(stream, tm[0], tm[1], p, a, grid, pl.smem);
+      else if (p.mode == U16_DECONV_PH && p.cpad == 4)
+        e = u16_launch_t<U16_DECONV_RGB>(stream, tm[0], tm[1], p, a, grid, pl.smem);
       else if (p.mode == U16_DECONV_PH)
         e = u16_launch_t<U16_DECONV_PH>(stream, tm[0], tm[1], p, a, grid, pl.smem);
       else

@@ -228,6 +228,23 @@ __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, in
     case IO_QUANT_U8:
     case IO_QUANT_F32: {
       const long long gp = (((long long)a.geo.n0 + n) * a.hout + y) * a.wout + x;
+      if (a.out_mode == IO_QUANT_U8 && NV == 16 && oc + NV <= a.cout && (a.cout & 15) == 0) {
+        // 16 symbols of one pixel are 16 consecutive bytes of the symbol tensor: one 16-byte store
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int s = tic_quantize_symbol(v[i], a.q);
+          w[i >> 2] |= (uint32_t)s << (8 * (i & 3));
+          if (a.q == 2) {
+            ones += s;
+            ++valid;
+          } else {
+            atomicAdd(&s_hist[s], 1u);
+          }
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.out) + gp * a.cout + oc) = make_uint4(w[0], w[1], w[2], w[3]);
+        break;
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (oc + i < a.cout) {

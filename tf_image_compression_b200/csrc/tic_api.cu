@@ -559,7 +559,7 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
   TIC_CUDA(h, cudaSetDevice(h->device));
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
   if (mem == TIC_MEM_DEVICE) {
-    upc *= 3;  // no staging to overlap with: fewer, longer launch sequences (12288 patches of 128x128 per sequence)
+    upc *= 4;  // no staging to overlap with: fewer, longer launch sequences (up to 16384 patches of 128x128 each)
     upc = (units + (units + upc - 1) / upc - 1) / ((units + upc - 1) / upc);  // equal-sized sequences
     for (int64_t u0 = 0; u0 < units; u0 += upc) {
       int64_t nu = std::min<int64_t>(upc, units - u0);

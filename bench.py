@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=int(os.environ.get("TIC_CHUNK", "0")), help="patches per launch sequence (0: library default)")
     ap.add_argument("--layers", action="store_true", help="print the per-layer time table to stderr")
+    ap.add_argument("--variant", default=VARIANT, help="model variant (default: model_0 = BASELINE config 2; e.g. base_model/ch_128 for config 3)")
+    ap.add_argument("--patch", type=int, default=P, help="patch size")
     return ap.parse_args()
 
 
@@ -344,7 +346,9 @@ def run_b200(args):
 
 
 def main():
+    global VARIANT, P
     args = parse()
+    VARIANT, P = args.variant, args.patch
     if args.impl == "reference":
         run_reference(args)
     else:

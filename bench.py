@@ -302,8 +302,16 @@ def run_b200(args):
         achieved = top["bytes_step"] / top["launches"] / top_launch_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
                     "peak_source": f"copy bandwidth, {pk['source']}"}
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists() and compute == "tensor":
+        # DRAM bytes of this kernel from the committed ncu --set full capture, scaled to this run's patches per launch
+        td = json.loads(tp.read_text())
+        per = td.get(VARIANT, {}).get(f"{top['graph']}/{top['scope']}")
+        if per is not None and P == 128:
+            traffic = per / td["patches_per_launch"] * npatch / top["launches"]
     roofline.update({
-        "traffic": None, "kernel": f"{top['graph']}/{top['scope']} ({compute})",
+        "traffic": traffic, "kernel": f"{top['graph']}/{top['scope']} ({compute})",
         "kernel_ms_per_launch": top_launch_s * 1e3, "kernel_share_of_step": top["ms_step"] / max(step_ms, 1e-9),
         "kernel_algorithmic_flop_per_byte": top["flops_step"] / top["bytes_step"], "ridge_flop_per_byte": ridge,
         "whole_step_algorithmic_tflops": world * sum(V.model_flops_per_pixel(VARIANT, P)) * pixels * args.steps / (ms_max * 1e-3) / 1e12,

@@ -128,6 +128,14 @@ int tic_decode_patches(tic_codec* h, const uint8_t* symbols, int64_t n, int hb, 
  * TIC_F32 keeps the float image (input of rmbe, submit/2/decoder.py:183-184). */
 int tic_decode_images(tic_codec* h, const uint8_t* symbols, int64_t n_images, int H, int W, int P,
                       void* images, int out_dtype, int mem);
+/* test.py:95-146 (compress_and_uncompress): encoder and decoder built in ONE graph, image in ->
+ * reconstruction out, no bitstream in between.  images [n_images,H,W,3] u8 -> symbols
+ * [n_images, gh*gw, h_b, w_b, c_b] u8 (may be NULL with host buffers: not copied back) and recon
+ * [n_images,H,W,3] (TIC_U8 rounded half-to-even | TIC_F32).  Results are identical to
+ * tic_encode_images followed by tic_decode_images; with host buffers the H2D of chunk i+1, the
+ * kernels of chunk i and the D2H of chunk i-1 overlap, so both PCIe directions are busy at once. */
+int tic_roundtrip_images(tic_codec* h, const uint8_t* images, int64_t n_images, int H, int W, int P,
+                         uint8_t* symbols, void* recon, int out_dtype, int mem);
 /* rmbe_model.model on [n,128,128,3] f32 tiles (submit/2/rmbe/model.py:113-197). */
 int tic_postfilter_patches(tic_codec* h, const float* tiles, int64_t n, int P, float* out, int mem);
 /* rmbe.rmbe(image) (submit/2/rmbe/rmbe.py:15-111): two in-place passes of 128x128 tiles offset

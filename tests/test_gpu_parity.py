@@ -378,3 +378,36 @@ def test_cfg5_model1_decode_and_rmbe(mode):
     assert torch.equal(img[:, :64, :64], before[:, :64, :64]) and not torch.equal(img[:, 64:192, 64:192], before[:, 64:192, 64:192])
     assert float(img.min()) >= 0.0 and float(img.max()) <= 255.0
     codec.close()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_roundtrip_equals_encode_then_decode(mode):
+    """tic_roundtrip_images (test.py:95-146, encoder and decoder in one graph) == tic_encode_images followed by
+    tic_decode_images, bit for bit: host buffers (streamed, several chunks, pinned and pageable), device buffers,
+    images that need reflect padding, float output, no symbol read-back; the histogram counts every symbol once."""
+    codec, enc, dec = make_codec("model_0", "fanin", compute=mode)
+    rs = np.random.RandomState(77)
+    imgs = rs.randint(0, 256, size=(5, 300, 410, 3), dtype=np.uint8)  # 3 x 4 patches per image, padded bottom / right
+    sym = codec.encode_images(imgs, 128)
+    rec = codec.decode_images(sym, 300, 410, 128)
+    codec.set_chunk_patches(24)  # host: 2 images per chunk -> 3 chunks, the last one ragged
+    codec.hist_reset()
+    r2, s2 = codec.roundtrip_images(imgs, 128)
+    assert np.array_equal(s2, sym) and np.array_equal(r2, rec)
+    assert int(codec.hist_read().sum()) == sym.size
+    pinned = torch.from_numpy(imgs).pin_memory()
+    out_p = torch.empty((5, 300, 410, 3), dtype=torch.uint8).pin_memory()
+    r3, s3 = codec.roundtrip_images(pinned, 128, out=out_p, want_symbols=False)
+    assert s3 is None and np.array_equal(r3.numpy(), rec)
+    rf, _ = codec.roundtrip_images(imgs, 128, out_dtype=np.float32)
+    assert np.array_equal(rf, codec.decode_images(sym, 300, 410, 128, out_dtype=np.float32))
+    rd, sd = codec.roundtrip_images(torch.from_numpy(imgs).cuda(), 128)
+    assert rd.is_cuda and np.array_equal(sd.cpu().numpy(), sym) and np.array_equal(rd.cpu().numpy(), rec)
+    # the oracle's round trip of one image (crop -> encoder -> decoder -> stitch -> np.around)
+    o = O.codec_roundtrip(imgs[1], "model_0", enc, dec, MEAN, STD, 2, 128)
+    o_img = o[1] if isinstance(o, tuple) else o
+    assert np.abs(o_img.astype(np.int32) - rec[1].astype(np.int32)).max() <= 1
+    from tf_image_compression_b200 import entry
+    outs = entry.compress_and_uncompress(codec, [imgs[0], imgs[1][:200, :256].copy(), imgs[2]], {"patch_size": 128})
+    assert np.array_equal(outs[0], rec[0]) and np.array_equal(outs[2], rec[2]) and outs[1].shape == (200, 256, 3)
+    codec.close()

@@ -281,6 +281,31 @@ class Codec:
                                                L.U8 if out_dtype == np.uint8 else L.F32, src.mem))
         return out
 
+    def roundtrip_images(self, images, patch_size, out=None, out_symbols=None, out_dtype=np.uint8, want_symbols=True):
+        """test.py:95-146 (compress_and_uncompress): encoder -> decoder in one call, [B,H,W,3] uint8 ->
+        (reconstruction [B,H,W,3] uint8 | float32, symbols [B, gh*gw, hb, wb, cb] uint8 | None).  Identical
+        results to encode_images + decode_images; host buffers stream through both PCIe directions at once."""
+        if images.ndim == 3:
+            images = images[None]
+        B, H, W = int(images.shape[0]), int(images.shape[1]), int(images.shape[2])
+        src = _Buf(images, np.uint8, self.device, self)
+        P = int(patch_size)
+        hb, wb, cb = self.bottleneck_shape(P)
+        gh, gw = -(-H // P), -(-W // P)
+        if out is None:
+            out = self._alloc_like(images, (B, H, W, 3), out_dtype)
+        else:
+            out_dtype = np.uint8 if str(out.dtype).endswith("uint8") else np.float32
+        dst = _Buf(out, out_dtype, self.device)
+        if out_symbols is None and (want_symbols or src.mem == L.MEM_DEVICE):
+            out_symbols = self._alloc_like(images, (B, gh * gw, hb, wb, cb), np.uint8)
+        sym = _Buf(out_symbols, np.uint8, self.device) if out_symbols is not None else None
+        if dst.mem != src.mem or (sym is not None and sym.mem != src.mem):
+            raise ValueError("input and outputs must all be host or all be device buffers")
+        self._check(self.lib.tic_roundtrip_images(self._h, src.ptr, B, H, W, P, sym.ptr if sym is not None else None,
+                                                  dst.ptr, L.U8 if out_dtype == np.uint8 else L.F32, src.mem))
+        return out, out_symbols
+
     def postfilter_patches(self, tiles, out=None):
         """rmbe_model.model on [N,P,P,3] float32 tiles."""
         if self.post_layers is None:

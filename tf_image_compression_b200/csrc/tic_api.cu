@@ -52,7 +52,7 @@ struct tic_codec {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_in[2]{}, ev_comp[2]{}, ev_out[2]{}, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_in[2]{}, ev_comp[2]{}, ev_out[2]{}, ev_enc[2]{}, ev_t0 = nullptr, ev_t1 = nullptr, ev_rt = nullptr;
   Graph g[3];
   int q = 0;
   float* d_symlut = nullptr;  // [256]
@@ -66,7 +66,8 @@ struct tic_codec {
   size_t bnd_bytes = 0;
   void* stage_in[2] = {nullptr, nullptr};
   void* stage_out[2] = {nullptr, nullptr};
-  size_t stage_in_bytes = 0, stage_out_bytes = 0;
+  void* stage_sym[2] = {nullptr, nullptr};      // round trips: the symbols between the two graphs
+  size_t stage_in_bytes = 0, stage_out_bytes = 0, stage_sym_bytes = 0;
   int64_t launches = 0;
   float last_ms = 0.f;
   bool profile = false;
@@ -549,12 +550,28 @@ int patches_per_chunk(const tic_codec* h, int P) {
   return std::max(1, c);
 }
 
+// Host-staged calls overlap H2D, kernels and D2H chunk by chunk; what does not overlap is the first chunk's H2D
+// and the last chunk's kernels + D2H, so chunks are equal-sized and small: at least `host_chunks` (8) of them as
+// long as a chunk keeps >= 1024 patches of 128x128 (enough tiles to fill 148 SMs in every layer).
+int64_t host_units_per_chunk(int64_t units, int64_t upc, double patches128_per_unit) {
+  static const int want = [] {
+    const char* e = getenv("TIC_HOST_CHUNKS");
+    const int v = e ? atoi(e) : 8;
+    return v < 1 ? 1 : v;
+  }();
+  int64_t chunks = (units + upc - 1) / upc;
+  const int64_t by_size = (int64_t)((double)units * patches128_per_unit / 1024.0);
+  chunks = std::max<int64_t>(chunks, std::min<int64_t>(want, by_size));
+  chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, units));
+  return (units + chunks - 1) / chunks;
+}
+
 // Generic chunked driver.  `units` are processed `upc` (units per chunk) at a time; a unit is a
 // patch or a whole image.  in_unit_bytes / out_unit_bytes describe the caller's buffers; run()
 // executes one chunk given device pointers (chunk-local when staged from host) and the unit offset.
 template <typename RunFn>
 int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64_t upc, size_t in_unit_bytes,
-          size_t out_unit_bytes, bool inout_same, RunFn run) {
+          size_t out_unit_bytes, bool inout_same, RunFn run, double patches128_per_unit = 1.0) {
   if (units <= 0) return TIC_OK;
   TIC_CUDA(h, cudaSetDevice(h->device));
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
@@ -570,6 +587,7 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
     return TIC_OK;
   }
   // host buffers: double-buffered staging, copies on side streams
+  upc = host_units_per_chunk(units, upc, patches128_per_unit);
   const size_t in_need = (size_t)upc * in_unit_bytes, out_need = (size_t)upc * out_unit_bytes;
   if (h->stage_in_bytes < in_need) {
     for (int b = 0; b < 2; ++b) {
@@ -627,6 +645,7 @@ Geo patch_geo(int P, long long n0) {
   g.ox = 0;
   g.P = P;
   g.n0 = n0;
+  geo_finish(g);
   return g;
 }
 
@@ -640,6 +659,7 @@ Geo image_geo(int H, int W, int P, long long n0) {
   g.ox = 0;
   g.P = P;
   g.n0 = n0;
+  geo_finish(g);
   return g;
 }
 
@@ -689,7 +709,9 @@ int tic_create(tic_codec** out, int device) {
     cudaEventCreateWithFlags(&h->ev_in[b], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_comp[b], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&h->ev_out[b], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_enc[b], cudaEventDisableTiming);
   }
+  cudaEventCreate(&h->ev_rt);
   cudaEventCreate(&h->ev_t0);
   cudaEventCreate(&h->ev_t1);
   if ((e = cudaMalloc(&h->d_hist, 256 * sizeof(unsigned long long))) != cudaSuccess) return bail("cudaMalloc", e);
@@ -721,10 +743,13 @@ void tic_destroy(tic_codec* h) {
   for (int b = 0; b < 2; ++b) {
     if (h->stage_in[b]) cudaFree(h->stage_in[b]);
     if (h->stage_out[b]) cudaFree(h->stage_out[b]);
+    if (h->stage_sym[b]) cudaFree(h->stage_sym[b]);
+    cudaEventDestroy(h->ev_enc[b]);
     cudaEventDestroy(h->ev_in[b]);
     cudaEventDestroy(h->ev_comp[b]);
     cudaEventDestroy(h->ev_out[b]);
   }
+  cudaEventDestroy(h->ev_rt);
   cudaEventDestroy(h->ev_t0);
   cudaEventDestroy(h->ev_t1);
   if (h->d_hist) cudaFree(h->d_hist);
@@ -901,7 +926,7 @@ int tic_encode_patches(tic_codec* h, const void* patches, int in_dtype, int64_t 
                  o.out = dout;
                  o.geo = patch_geo(P, u0);
                  return run_graph(h, TIC_GRAPH_ENCODER, i, o, (int)nu, P, P);
-               });
+               }, (double)P * P / 16384.0);
 }
 
 int tic_encode_images(tic_codec* h, const uint8_t* images, int64_t n_images, int H, int W, int P, uint8_t* symbols,
@@ -932,7 +957,7 @@ int tic_encode_images(tic_codec* h, const uint8_t* images, int64_t n_images, int
                  o.out = dout;
                  o.geo = i.geo;
                  return run_graph(h, TIC_GRAPH_ENCODER, i, o, (int)(nu * ppi), P, P);
-               });
+               }, (double)ppi * P * P / 16384.0);
 }
 
 int tic_decode_patches(tic_codec* h, const uint8_t* symbols, int64_t n, int hb, int wb, float* recon, int mem) {
@@ -957,7 +982,7 @@ int tic_decode_patches(tic_codec* h, const uint8_t* symbols, int64_t n, int hb, 
                  o.out = dout;
                  o.geo = patch_geo(P, u0);
                  return run_graph(h, TIC_GRAPH_DECODER, i, o, (int)nu, hb, wb);
-               });
+               }, (double)P * P / 16384.0);
 }
 
 int tic_decode_images(tic_codec* h, const uint8_t* symbols, int64_t n_images, int H, int W, int P, void* images,
@@ -995,7 +1020,110 @@ int tic_decode_images(tic_codec* h, const uint8_t* symbols, int64_t n_images, in
                  o.out = dout;
                  o.geo = i.geo;
                  return run_graph(h, TIC_GRAPH_DECODER, i, o, (int)(nu * ppi), hb, wb);
-               });
+               }, (double)ppi * P * P / 16384.0);
+}
+
+int tic_roundtrip_images(tic_codec* h, const uint8_t* images, int64_t n_images, int H, int W, int P, uint8_t* symbols,
+                         void* recon, int out_dtype, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n_images < 0 || H <= 0 || W <= 0 || P <= 0 || (n_images > 0 && (!images || !recon)))
+    return fail(h, TIC_ERR_INVALID, "bad arguments");
+  if (out_dtype != TIC_U8 && out_dtype != TIC_F32) return fail(h, TIC_ERR_INVALID, "bad out_dtype");
+  if (mem == TIC_MEM_DEVICE) {
+    if (!symbols && n_images > 0) return fail(h, TIC_ERR_INVALID, "device-resident round trips need a symbol buffer");
+    int rc = tic_encode_images(h, images, n_images, H, W, P, symbols, mem);
+    if (rc != TIC_OK) return rc;
+    cudaEvent_t t0 = h->ev_t0;  // keep the encoder's start event: last_kernel_ms covers both graphs
+    h->ev_t0 = h->ev_rt;
+    rc = tic_decode_images(h, symbols, n_images, H, W, P, recon, out_dtype, mem);
+    h->ev_rt = h->ev_t0;
+    h->ev_t0 = t0;
+    return rc;
+  }
+  if ((H % P != 0 && H < 2) || (W % P != 0 && W < 2)) return fail(h, TIC_ERR_INVALID, "reflect padding needs at least 2 pixels");
+  int rc = check_graph_ready(h, TIC_GRAPH_ENCODER, true);
+  if (rc != TIC_OK) return rc;
+  rc = check_graph_ready(h, TIC_GRAPH_DECODER, true);
+  if (rc != TIC_OK) return rc;
+  if (h->q < 2) return fail(h, TIC_ERR_STATE, "quantiser not configured (tic_set_quantizer)");
+  if (h->g[TIC_GRAPH_ENCODER].layers[0].d.cin != 3) return fail(h, TIC_ERR_INVALID, "encoder must take 3 channels");
+  int hb, wb, cb;
+  rc = tic_bottleneck_shape(h, P, &hb, &wb, &cb);
+  if (rc != TIC_OK) return rc;
+  Graph& gd = h->g[TIC_GRAPH_DECODER];
+  Shape so;
+  if (gd.layers[0].d.cin != cb || graph_out_shape(gd, Shape{hb, wb, cb}, &so, nullptr) != 0 || so.c != 3 || so.h != P || so.w != P)
+    return fail(h, TIC_ERR_INVALID, "decoder graph does not map the encoder's %dx%dx%d symbols back to %dx%d RGB", hb, wb, cb, P, P);
+  if (n_images == 0) return TIC_OK;
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  const Geo g0 = image_geo(H, W, P, 0);
+  const int ppi = g0.gh * g0.gw;
+  const int64_t ipc = host_units_per_chunk(n_images, std::max<int64_t>(1, patches_per_chunk(h, P) / ppi), (double)ppi * P * P / 16384.0);
+  const size_t img_unit = (size_t)H * W * 3;
+  const size_t sym_unit = (size_t)ppi * hb * wb * cb;
+  const size_t rec_unit = img_unit * (out_dtype == TIC_U8 ? 1 : 4);
+  auto grow = [&](void** bufs, size_t* have, size_t need) -> int {
+    if (*have >= need) return TIC_OK;
+    TIC_CUDA(h, cudaDeviceSynchronize());
+    for (int b = 0; b < 2; ++b) {
+      if (bufs[b]) cudaFree(bufs[b]);
+      bufs[b] = nullptr;
+    }
+    *have = 0;
+    for (int b = 0; b < 2; ++b) TIC_CUDA(h, cudaMalloc(&bufs[b], need));
+    *have = need;
+    return TIC_OK;
+  };
+  if ((rc = grow(h->stage_in, &h->stage_in_bytes, (size_t)ipc * img_unit)) != TIC_OK) return rc;
+  if ((rc = grow(h->stage_sym, &h->stage_sym_bytes, (size_t)ipc * sym_unit)) != TIC_OK) return rc;
+  if ((rc = grow(h->stage_out, &h->stage_out_bytes, (size_t)ipc * rec_unit)) != TIC_OK) return rc;
+  // Three streams, two staging sets: H2D of chunk i+1 (one PCIe direction) runs under the kernels of chunk i and
+  // the D2H of chunk i-1 (the other direction).
+  TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
+  int64_t idx = 0;
+  for (int64_t u0 = 0; u0 < n_images; u0 += ipc, ++idx) {
+    const int b = (int)(idx & 1);
+    const int64_t nu = std::min<int64_t>(ipc, n_images - u0);
+    if (idx >= 2) TIC_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_enc[b], 0));  // encoder of chunk idx-2 consumed stage_in[b]
+    TIC_CUDA(h, cudaMemcpyAsync(h->stage_in[b], images + (size_t)u0 * img_unit, (size_t)nu * img_unit, cudaMemcpyHostToDevice,
+                                h->s_h2d));
+    TIC_CUDA(h, cudaEventRecord(h->ev_in[b], h->s_h2d));
+    TIC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_in[b], 0));
+    if (idx >= 2) TIC_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_out[b], 0));  // stage_sym / stage_out[b] drained
+    IoSpec i, o;
+    i.mode = IO_U8_NORM;
+    i.in = h->stage_in[b];
+    i.geo = image_geo(H, W, P, 0);
+    o.mode = IO_QUANT_U8;
+    o.out = h->stage_sym[b];
+    o.geo = i.geo;
+    rc = run_graph(h, TIC_GRAPH_ENCODER, i, o, (int)(nu * ppi), P, P);
+    if (rc != TIC_OK) return rc;
+    TIC_CUDA(h, cudaEventRecord(h->ev_enc[b], h->stream));
+    IoSpec di, dout;
+    di.mode = IO_U8_SYMLUT;
+    di.in = h->stage_sym[b];
+    di.geo = i.geo;
+    dout.mode = out_dtype == TIC_U8 ? IO_DENORM_U8 : IO_DENORM_F32;
+    dout.out = h->stage_out[b];
+    dout.geo = i.geo;
+    rc = run_graph(h, TIC_GRAPH_DECODER, di, dout, (int)(nu * ppi), hb, wb);
+    if (rc != TIC_OK) return rc;
+    TIC_CUDA(h, cudaEventRecord(h->ev_comp[b], h->stream));
+    if (symbols) {
+      TIC_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_enc[b], 0));
+      TIC_CUDA(h, cudaMemcpyAsync(symbols + (size_t)u0 * sym_unit, h->stage_sym[b], (size_t)nu * sym_unit, cudaMemcpyDeviceToHost,
+                                  h->s_d2h));
+    }
+    TIC_CUDA(h, cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+    TIC_CUDA(h, cudaMemcpyAsync((char*)recon + (size_t)u0 * rec_unit, h->stage_out[b], (size_t)nu * rec_unit, cudaMemcpyDeviceToHost,
+                                h->s_d2h));
+    TIC_CUDA(h, cudaEventRecord(h->ev_out[b], h->s_d2h));
+  }
+  TIC_CUDA(h, cudaEventRecord(h->ev_t1, h->stream));
+  TIC_CUDA(h, cudaStreamSynchronize(h->s_d2h));
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return TIC_OK;
 }
 
 int tic_postfilter_patches(tic_codec* h, const float* tiles, int64_t n, int P, float* out, int mem) {
@@ -1057,6 +1185,7 @@ int tic_postfilter_images(tic_codec* h, float* images, int64_t n_images, int H, 
                    const int tiles = gg.gh * gg.gw;
                    if (tiles <= 0) continue;
                    gg.n0 = u0 * tiles;
+                   geo_finish(gg);
                    IoSpec i, o;
                    i.mode = IO_F32_NORM;
                    i.in = dout;  // in place: pass 2 reads what pass 1 wrote

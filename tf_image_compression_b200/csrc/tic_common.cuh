@@ -21,6 +21,36 @@ enum IoMode : int {
   IO_ACT16 = 8         // fp16 pair planes (hi, lo' = (x - hi) * 2048) of an NHWC activation (tic_umma16.cuh)
 };
 
+// Division by a launch constant.  A 32-bit `/` by a kernel parameter compiles to a ~20-instruction reciprocal
+// routine (a 64-bit one to ~4x that); the tile -> (patch, row, column) -> image decode runs once per tile in every
+// lane of the builder and epilogue warps, where it was a third of all issued instructions (profiles/r1e_*).
+// Round-up multiplier method: exact for dividends below 2^31 (launchers check the tile / patch counts).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+  }
+  return f;
+}
+__host__ __device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv& f) {
+#ifdef __CUDA_ARCH__
+  return f.d == 1 ? n : __umulhi(n, f.mul) >> f.shr;
+#else
+  return f.d == 1 ? n : (uint32_t)(((uint64_t)n * f.mul) >> 32) >> f.shr;
+#endif
+}
+__host__ __device__ __forceinline__ void fast_divmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = fast_div(n, f);
+  r = n - q * f.d;
+}
+
 // Patch <-> image geometry.  A "patch array" [n,P,P,3] is the degenerate case
 // H = W = P, gh = gw = 1.  utils.crop_image_input_patches (utils/utils.py:96-133) pads
 // bottom/right with np.pad(...,'reflect') and walks the patch grid row-major;
@@ -32,7 +62,18 @@ struct Geo {
   int oy, ox;    // origin of the grid inside the image
   int P;         // patch edge
   long long n0;  // global index of the chunk's first patch
+  FastDiv per_img_d, gw_d;  // / (gh * gw), / gw  (geo_finish)
 };
+inline void geo_finish(Geo& g) {
+  g.per_img_d = make_fastdiv((uint32_t)(g.gh * g.gw > 0 ? g.gh * g.gw : 1));
+  g.gw_d = make_fastdiv((uint32_t)(g.gw > 0 ? g.gw : 1));
+}
+// global patch -> (image, grid row, grid column)
+__device__ __forceinline__ void geo_decode(const Geo& g, unsigned patch, unsigned& img, unsigned& gy, unsigned& gx) {
+  unsigned r;
+  fast_divmod(patch, g.per_img_d, img, r);
+  fast_divmod(r, g.gw_d, gy, gx);
+}
 
 __device__ __forceinline__ int reflect_index(int i, int n) {
   // numpy 'reflect' (no edge repeat): period 2(n-1)
@@ -47,11 +88,8 @@ __device__ __forceinline__ int reflect_index(int i, int n) {
 // when outside the image and reflect == false.
 __device__ __forceinline__ long long geo_pixel(const Geo& g, long long patch, int y, int x, bool reflect) {
   // 32-bit index arithmetic (host guarantees patch < 2^31); only the final offset is 64-bit
-  const unsigned per_img = (unsigned)(g.gh * g.gw);
-  const unsigned pt = (unsigned)patch;
-  const unsigned img = pt / per_img;
-  const unsigned r = pt - img * per_img;
-  const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+  unsigned img, gy, gx;
+  geo_decode(g, (unsigned)patch, img, gy, gx);
   int Y = g.oy + (int)gy * g.P + y;
   int X = g.ox + (int)gx * g.P + x;
   if (reflect) {

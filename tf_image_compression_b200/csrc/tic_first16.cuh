@@ -25,6 +25,7 @@ struct F16Params {
   int stride, pad;       // TF SAME: stride 2 on even maps pads (0, 1); stride 1 pads (1, 1)
   int bn, bh;
   int tiles_x, tiles_y;
+  FastDiv tx_d, ty_d, txy_d;  // / tiles_x, / tiles_y, / (tiles_x * tiles_y)
   long long num_tiles;
   int npad;
   int nbuf;              // TMEM tile buffers (power of two, <= 4)
@@ -108,21 +109,17 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
     const int hh = grp / p.bn, nb = grp % p.bn;
     const uint32_t sw = (uint32_t)((m >> 1) & 3);
     const Geo g = a.geo;
-    const unsigned per_img = (unsigned)(g.gh * g.gw);
     uint32_t it = (uint32_t)group;
     for (long long tile = blockIdx.x + (long long)group * gridDim.x; tile < p.num_tiles; tile += 2LL * gridDim.x, it += 2) {
-      long long tt = tile;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
-      const int oy = ty * p.bh + hh, ox = tx * 8 + xx;
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tile, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n = (int)tn * p.bn + nb;
+      const int oy = (int)ty * p.bh + hh, ox = (int)tx * 8 + xx;
       // patch -> image geometry (utils/utils.py:96-133); reflect only ever fires on padded image borders
       const bool nok = n < p.n;
-      const unsigned gp = (unsigned)(g.n0 + (nok ? n : 0));
-      const unsigned img = gp / per_img;
-      const unsigned r = gp - img * per_img;
-      const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+      unsigned img, gy, gx;
+      geo_decode(g, (unsigned)(g.n0 + (nok ? n : 0)), img, gy, gx);
       const int Y0 = g.oy + (int)gy * g.P, X0 = g.ox + (int)gx * g.P;
       const long long img_off = (long long)img * g.H * g.W;
       long long off[9];
@@ -240,17 +237,16 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
       const uint32_t b = it & bmask;
       ptx::mbar_wait(&bars->acc_full[b], (it >> nbshift) & 1);
       ptx::tc_fence_after();
-      long long tt = tile;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tile, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n = (int)tn * p.bn + nb;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
       if (staged)
-        u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * p.bh + hh, tx * 8 + xx, n < p.n, s_bias,
+        u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * p.bh + hh, (int)tx * 8 + xx, n < p.n, s_bias,
                                          s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0);
       else
-        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * p.bh + hh, tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
+        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * p.bh + hh, (int)tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
                                   h_valid);
       ptx::tc_fence_before();
       __syncwarp();
@@ -369,21 +365,16 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
     // per thread.  The gather is latency-bound, so the raw bytes of tile i+1 are requested before tile i is
     // converted; tiles whose window lies inside the image skip the reflect arithmetic. =====
     const Geo g = a.geo;
-    const unsigned per_img = (unsigned)(g.gh * g.gw);
     const bool u8in = a.in_mode == IO_U8_NORM;
     const int ry = tid / 6, cx0 = (tid - ry * 6) * 3;
     const bool rowt = ry < kW2Rows;
-    const unsigned tiles_xy = (unsigned)(p.tiles_x * p.tiles_y);
     const unsigned thread_off = (unsigned)(ry * g.W + cx0) * 3u;
     auto request = [&](unsigned tile, uint32_t (&raw)[9], unsigned& okm) {
       // warp-uniform part: tile -> patch -> image window
-      const unsigned n = tile / tiles_xy;
-      const unsigned rt = tile - n * tiles_xy;
-      const unsigned ty = rt / (unsigned)p.tiles_x, tx = rt - ty * (unsigned)p.tiles_x;
-      const unsigned gp = (unsigned)g.n0 + n;
-      const unsigned img = gp / per_img;
-      const unsigned r = gp - img * per_img;
-      const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+      unsigned n, rt, ty, tx, img, gy, gx;
+      fast_divmod(tile, p.txy_d, n, rt);
+      fast_divmod(rt, p.tx_d, ty, tx);
+      geo_decode(g, (unsigned)g.n0 + n, img, gy, gx);
       const int iy0 = 32 * (int)ty, ix0 = 16 * (int)tx;                               // patch-local window origin
       const int Yb = g.oy + (int)gy * g.P + iy0, Xb = g.ox + (int)gx * g.P + ix0;     // image window origin
       const long long img_off = (long long)img * g.H * g.W;
@@ -530,17 +521,16 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
       const uint32_t b = it & bmask;
       ptx::mbar_wait(&bars->acc_full[b], (it >> nbshift) & 1);
       ptx::tc_fence_after();
-      long long tt = tile;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n = (int)(tt / p.tiles_y);
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tile, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n = (int)tn;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
       if (staged)
-        u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * 16 + hh, tx * 8 + xx, true, s_bias,
+        u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, s_bias,
                                          s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0);
       else
-        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, ty * 16 + hh, tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
+        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
@@ -604,6 +594,10 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   p.tiles_x = a.wout / 8;
   p.tiles_y = a.hout / p.bh;
   p.num_tiles = (long long)p.tiles_x * p.tiles_y * ((a.n + p.bn - 1) / p.bn);
+  if (p.num_tiles >= (1LL << 31) - 65536) return fail("too many tiles for one launch", -5);
+  p.tx_d = make_fastdiv((uint32_t)p.tiles_x);
+  p.ty_d = make_fastdiv((uint32_t)p.tiles_y);
+  p.txy_d = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
   p.npad = a.cout;
   p.nbuf = std::min(4, 512 / (2 * p.npad));
   const bool windowed = stride == 2 && p.bn == 1;  // operands straight from the staged input tile (no im2col)

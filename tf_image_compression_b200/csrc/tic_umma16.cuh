@@ -62,6 +62,7 @@ struct U16Params {
   int Ht, Wt;            // tile-space map (S1/S2: output map, DECONV: input map)
   int bn, bh;            // patches per tile (1 | 2), map rows per tile per patch (16 | 8)
   int tiles_x, tiles_y;
+  FastDiv tx_d, ty_d;    // / tiles_x, / tiles_y
   long long num_tiles;
   int KB;                // K-blocks (input-channel chunks of kc)
   int kc;                // channels per K-block
@@ -314,11 +315,8 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
     if (a.out_mode == IO_DENORM_U8 || a.out_mode == IO_DENORM_F32) {
       // patch -> image geometry once per pixel pair (utils.concat_patches, utils/utils.py:136-167: crop to [H, W])
       const Geo& g = a.geo;
-      const unsigned per_img = (unsigned)(g.gh * g.gw);
-      const unsigned gp = (unsigned)(g.n0 + n);
-      const unsigned img = gp / per_img;
-      const unsigned r = gp - img * per_img;
-      const unsigned gy = r / (unsigned)g.gw, gx = r - gy * (unsigned)g.gw;
+      unsigned img, gy, gx;
+      geo_decode(g, (unsigned)(g.n0 + n), img, gy, gx);
       const int Y = g.oy + (int)gy * g.P + 2 * yt + half, X = g.ox + (int)gx * g.P + 2 * xt;
       if (Y >= g.H) return;
       const long long off = (((long long)img * g.H + Y) * g.W + X) * 3;
@@ -742,11 +740,11 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       long long tt = tile;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n0 = (int)(tt / p.tiles_y) * p.bn;
-      const int x0 = tx * 8, y0 = ty * p.bh;
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tt, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n0 = (int)tn * p.bn;
+      const int x0 = (int)tx * 8, y0 = (int)ty * p.bh;
       for (int kb = 0; kb < p.KB; ++kb) {
         for (int plane = 0; plane < 2; ++plane, ++it) {
           const int s = it % p.S;
@@ -822,11 +820,11 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
       ptx::tc_fence_after();
       long long tt = tile;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
-      const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tt, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n = (int)tn * p.bn + nb;
+      const int yt = (int)ty * p.bh + hh, xt = (int)tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
       if (p.staged)
@@ -937,11 +935,11 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint32_t it = 0;
     for (long long tp = pair0; tp < num_pairs; tp += npairs) {
       long long tt = 2 * tp + rank;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n0 = (int)(tt / p.tiles_y) * p.bn;
-      const int x0 = tx * 8, y0 = ty * p.bh;
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tt, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n0 = (int)tn * p.bn;
+      const int x0 = (int)tx * 8, y0 = (int)ty * p.bh;
       for (int kb = 0; kb < p.KB; ++kb) {
         for (int plane = 0; plane < 2; ++plane, ++it) {
           const int s = it % p.S;
@@ -1019,11 +1017,11 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
       ptx::tc_fence_after();
       long long tt = 2 * tp + rank;
-      const int tx = (int)(tt % p.tiles_x);
-      tt /= p.tiles_x;
-      const int ty = (int)(tt % p.tiles_y);
-      const int n = (int)(tt / p.tiles_y) * p.bn + nb;
-      const int yt = ty * p.bh + hh, xt = tx * 8 + xx;
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tt, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      const int n = (int)tn * p.bn + nb;
+      const int yt = (int)ty * p.bh + hh, xt = (int)tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
       if (p.staged)
@@ -1127,6 +1125,9 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   p.tiles_x = p.Wt / 8;
   p.tiles_y = p.Ht / p.bh;
   p.num_tiles = (long long)p.tiles_x * p.tiles_y * ((a.n + p.bn - 1) / p.bn);
+  if (p.num_tiles >= (1LL << 31) - 65536) return false;  // FastDiv range (and the 32-bit tile counters)
+  p.tx_d = make_fastdiv((uint32_t)p.tiles_x);
+  p.ty_d = make_fastdiv((uint32_t)p.tiles_y);
   p.kc = std::min(a.cin, 64);
   p.KB = a.cin / p.kc;
   p.ksteps = p.kc / 16;

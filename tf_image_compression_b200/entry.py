@@ -1,5 +1,6 @@
 """The reference's entry-point flows on top of the B200 path: compress (encode.py:125-212), uncompress
-(decode.py:143-251, with the submit/2 post-filter call order submit/2/decoder.py:183-198) and the dataset-wide
+(decode.py:143-251, with the submit/2 post-filter call order submit/2/decoder.py:183-198), the one-graph round
+trip (test.py:95-146) and the dataset-wide
 symbol table (get_encoded_distribution.py:85-155).  File names, config keys, table construction and the
 bitstream order (patch-major, then h, w, c: encode.py:171-182) are the reference's; images are processed in
 batches through Codec.encode_images / decode_images instead of one sess.run per 64 patches."""
@@ -94,6 +95,23 @@ def uncompress(codec, input_dir, config, prob, postfilter=False):
         for k, (stem, _) in enumerate(items):
             result[stem] = rec[k]
     return result
+
+
+def compress_and_uncompress(codec, images, config):
+    """test.py:95-146: encoder and decoder in one graph, no bitstream — the reference's quality check.  Images of
+    equal size go through Codec.roundtrip_images as one batch.  Returns the uint8 reconstructions in input order
+    (io.imsave of the stitched float image rounds like decode.py:249)."""
+    P = int(config["patch_size"])
+    out = [None] * len(images)
+    by_shape = {}
+    for i, im in enumerate(images):
+        by_shape.setdefault(tuple(im.shape), []).append(i)
+    for shape, idx in by_shape.items():
+        batch = np.ascontiguousarray(np.stack([images[i] for i in idx]), dtype=np.uint8)
+        rec, _ = codec.roundtrip_images(batch, P, want_symbols=False)
+        for k, i in enumerate(idx):
+            out[i] = rec[k]
+    return out
 
 
 def get_distribution(codec, patches, group=None):

@@ -175,6 +175,9 @@ float tic_last_kernel_ms(const tic_codec* h);
 int tic_profile_enable(tic_codec* h, int on);
 int tic_profile_reset(tic_codec* h);
 int tic_profile_read(tic_codec* h, int graph, float* ms, int64_t* launches, int n_layers);
+/* CRC-32C (Castagnoli, reflected, init/xorout 0xffffffff) of a host buffer: the checksum of the TF-V2 checkpoint
+ * bundle that utils.restore_params reads (utils/utils.py:84-93; tf_image_compression_b200/checkpoint.py). */
+uint32_t tic_crc32c(const void* data, uint64_t n);
 const char* tic_version(void);
 
 #ifdef __cplusplus

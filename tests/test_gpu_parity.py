@@ -411,3 +411,23 @@ def test_roundtrip_equals_encode_then_decode(mode):
     outs = entry.compress_and_uncompress(codec, [imgs[0], imgs[1][:200, :256].copy(), imgs[2]], {"patch_size": 128})
     assert np.array_equal(outs[0], rec[0]) and np.array_equal(outs[2], rec[2]) and outs[1].shape == (200, 256, 3)
     codec.close()
+
+
+def test_restore_params_from_tf_v2_checkpoint(tmp_path):
+    """utils.restore_params (utils/utils.py:84-93): model_N/params_for_test/params written in the TF-V2 bundle layout
+    -> checkpoint.restore_params -> the same symbols and reconstruction as the codec given the arrays directly."""
+    from tf_image_compression_b200 import checkpoint as K
+    codec, enc, dec = make_codec("model_0", "fanin", compute="tensor")
+    patches = patches_from_images(1, 256, 256, 128, seed=3)
+    sym = codec.encode_patches(patches)
+    rec = codec.decode_patches(sym)
+    codec.close()
+    K.write_checkpoint(tmp_path / "model_0" / "params_for_test" / "params", {**enc, **dec})
+    fresh = T.Codec("model_0", quan_scale=2, mean=MEAN, std=STD, compute="tensor", seed=5)  # reference-init weights
+    assert not np.array_equal(fresh.encode_patches(patches), sym)
+    K.restore_params(fresh, model_num=0, root=str(tmp_path))
+    assert np.array_equal(fresh.encode_patches(patches), sym)
+    assert np.array_equal(fresh.decode_patches(sym), rec)
+    with pytest.raises(FileNotFoundError):
+        K.restore_params(fresh, params_file=str(tmp_path / "absent" / "params"))
+    fresh.close()

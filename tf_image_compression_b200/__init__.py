@@ -6,4 +6,4 @@ from .codec import Codec, TicError, inverse_sigmoid_lut, reference_init  # noqa:
 from .model_api import ModelModule, load_config, load_normalization  # noqa: F401
 from . import utils  # noqa: F401
 from . import rmbe  # noqa: F401
-from . import parallel, range_coder, entry  # noqa: F401
+from . import parallel, range_coder, entry, checkpoint  # noqa: F401

@@ -58,6 +58,7 @@ SIGNATURES = {
     "tic_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "tic_profile_reset": (C.c_int, [C.c_void_p]),
     "tic_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]),
+    "tic_crc32c": (C.c_uint32, [C.c_char_p, C.c_uint64]),
     "tic_version": (C.c_char_p, []),
 }
 

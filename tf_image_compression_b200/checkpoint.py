@@ -304,10 +304,10 @@ def write_checkpoint(prefix, tensors, block_size=4096):
     offset = 0
     with open(prefix + ".data-00000-of-00001", "wb") as f:
         for name in sorted(tensors, key=lambda s: s.encode("utf-8")):
-            a = np.ascontiguousarray(tensors[name])
+            a = np.asarray(tensors[name])  # (ascontiguousarray would turn a scalar into shape (1,))
             if a.dtype not in _DTYPE_IDS:
                 raise CheckpointError(f"{name}: dtype {a.dtype} has no TF enum here")
-            raw = a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes()
+            raw = a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes(order="C")
             shape = b"".join(_msg(2, _field(1, 0, _put_varint(int(d)))) for d in a.shape)
             entry = _field(1, 0, _put_varint(_DTYPE_IDS[a.dtype])) + _msg(2, shape)
             if offset:

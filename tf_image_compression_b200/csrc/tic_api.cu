@@ -1338,6 +1338,35 @@ int tic_profile_read(tic_codec* h, int graph, float* ms, int64_t* launches, int 
   return TIC_OK;
 }
 
+uint32_t tic_crc32c(const void* data, uint64_t n) {
+  static uint32_t table[8][256];
+  static const bool ready = [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xffu];
+    return true;
+  }();
+  (void)ready;
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = 0xffffffffu;
+  while (n >= 8) {  // slicing-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xffu] ^ table[6][(lo >> 8) & 0xffu] ^ table[5][(lo >> 16) & 0xffu] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xffu] ^ table[2][(hi >> 8) & 0xffu] ^ table[1][(hi >> 16) & 0xffu] ^ table[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ table[0][(c ^ *p++) & 0xffu];
+  return c ^ 0xffffffffu;
+}
+
 int64_t tic_launch_count(const tic_codec* h) { return h ? h->launches : 0; }
 
 float tic_last_kernel_ms(const tic_codec* h) {

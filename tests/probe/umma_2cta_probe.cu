@@ -12,10 +12,6 @@ using namespace tic::ptx;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
@@ -25,18 +21,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo, uint3
   d |= (uint64_t)layout << 61;
   return d;
 }
-__device__ __forceinline__ void mma2_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2_kernel(int N, int count, int R, long long* cycles) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2_kernel(int N, int count, int R, long long* cycles, uint32_t layout, uint32_t sbo, uint32_t a_start) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t rank = cluster_rank();
-  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = tid; i < (32768 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (tid == 0) { mbar_init(&bar_mma, 1); fence_barrier_init(); }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(512) : "memory");
@@ -49,8 +40,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2_kernel(in
   tc_fence_after();
   if (warp == 1 && rank == 0) {
     const uint32_t idesc = make_idesc_f16(256, N);
-    const uint64_t ad0 = make_desc(smem_u32(smem), 1024, 2);
-    const uint64_t bd0 = make_desc(smem_u32(smem + 16384), 1024, 2);
+    // A: `layout` rows (2 = SWIZZLE_128B, 4 = 64B, 6 = 32B), 8-row groups `sbo` bytes apart, start offset a_start
+    // (the "one box, nine taps" operands of tic_umma16.cuh start on arbitrary rows: sbo = 9 or 10 rows)
+    const uint64_t ad0 = make_desc(smem_u32(smem) + a_start, sbo, layout);
+    const uint64_t bd0 = make_desc(smem_u32(smem + 32768), layout == 2 ? 1024 : layout == 4 ? 512 : 256, layout);
     long long t0 = clock64();
     uint32_t r = 0;
     for (int i = 0; i < count; i += 4) {
@@ -80,7 +73,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128) rate2_kernel(in
 }
 
 int main() {
-  const size_t smem_bytes = 16384 + 32768;
+  const size_t smem_bytes = 32768 + 32768;
   CK(cudaFuncSetAttribute(rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   long long* d_cyc;
   CK(cudaMalloc(&d_cyc, 16));
@@ -88,13 +81,28 @@ int main() {
     for (int R : {1, 2}) {
       if (R * N > 512) continue;
       const int count = 4096;
-      rate2_kernel<<<2, 128, smem_bytes>>>(N, count, R, d_cyc);
+      rate2_kernel<<<2, 128, smem_bytes>>>(N, count, R, d_cyc, 2u, 1024u, 0u);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("kernel error %s (N=%d)\n", cudaGetErrorString(e), N); return 3; }
       long long c[2];
       CK(cudaMemcpy(c, d_cyc, 16, cudaMemcpyDeviceToHost));
       printf("2CTA f16 K=16 M=256 N=%3d R=%d: issue %.1f cyc/MMA, complete %.1f cyc/MMA  -> %.0f MAC/cycle/SM (ideal %d cycles)\n", N, R,
              (double)c[0] / count, (double)c[1] / count, 128.0 * N * 16 / ((double)c[1] / count), N / 2);
+    }
+  // operand layouts of the 32-channel layers (64-byte rows) against the 64-channel ones (128-byte rows)
+  struct Cfg { const char* name; uint32_t layout, sbo, start; };
+  const Cfg cfgs[] = {{"SW128 sbo=1024", 2, 1024, 0},     {"SW128 sbo=1280 (10-col box) start=128", 2, 1280, 128},
+                      {"SW64  sbo=512", 4, 512, 0},       {"SW64  sbo=576 (9-col box) start=64", 4, 576, 64},
+                      {"SW64  sbo=640 (10-col box) start=64", 4, 640, 64}, {"SW32  sbo=256", 6, 256, 0}};
+  for (const Cfg& c : cfgs)
+    for (int N : {16, 32, 64, 128}) {
+      const int count = 4096;
+      rate2_kernel<<<2, 128, smem_bytes>>>(N, count, 1, d_cyc, c.layout, c.sbo, c.start);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("kernel error %s (%s N=%d)\n", cudaGetErrorString(e), c.name, N); return 3; }
+      long long cy[2];
+      CK(cudaMemcpy(cy, d_cyc, 16, cudaMemcpyDeviceToHost));
+      printf("2CTA f16 K=16 M=256 N=%3d %-40s: %.1f cyc/MMA\n", N, c.name, (double)cy[1] / count);
     }
   return 0;
 }

@@ -91,6 +91,7 @@ struct U16Params {
   uint32_t wA_bytes;     // pair: per-CTA bytes of its half of the stacked weight tiles (all taps, K-blocks)
   uint32_t wB_bytes;     // pair: per-CTA bytes of its half of W_hi for the A_lo' x W_hi product
   long long in_lo_off;   // elements between the hi and lo' planes of the input (unused by the kernel: second tensor map)
+  int dbg;               // measurement aid (env TIC_DBG, pair kernel): 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue work
 };
 
 struct U16WeightSlice {
@@ -649,43 +650,55 @@ __device__ __forceinline__ void u16_epilogue_tile_staged(const LayerArgs& a, con
     u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad);
 }
 
-template <int MODE, bool PAIR = false>
-__device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
-                                                uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
-                                                uint32_t tapw, int ksteps, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
-                                                bool fresh_kb) {
+// KS = MMAs (K = 16) per tap and K-block, compile-time: with a run-time bound the unrolled body carries four
+// predicated instruction groups per tap, and the issuing warp's instruction stream — not the tensor pipe — is what
+// bounds the layers with small N (TIC_DBG=6: 105 cycles per MMA in decode_0 against 58 in the rate probe).
+template <int MODE, bool PAIR, int KS>
+__device__ __forceinline__ void u16_issue_plane_t(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
+                                                  uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
+                                                  uint32_t tapw, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
+                                                  bool fresh_kb) {
 #pragma unroll
   for (int tap = 0; tap < (u16_is_ph(MODE) ? 4 : 9); ++tap) {  // PH: tap = view
     const uint32_t ad = abase + (p.a_off[tap] >> 4);
     const uint32_t bd = wbase + (uint32_t)tap * tapw;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      if (ks < ksteps) {
-        uint32_t d, accumulate;
-        if (u16_is_ph(MODE)) {
-          d = dplane;
-          accumulate = (fresh_kb && tap == 0 && ks == 0) ? 0u : 1u;
-        } else if (MODE == U16_DECONV) {
-          constexpr int dummy = 0;
-          (void)dummy;
-          const int kh = tap / 3, kw = tap - kh * 3;
-          const uint32_t ph = (uint32_t)((kh == 1) * 2 + (kw == 1));
-          d = dplane + ph * pairw;
-          const bool first_tap = (tap == 0 || tap == 1 || tap == 3 || tap == 4);
-          accumulate = (fresh_kb && first_tap && ks == 0) ? 0u : 1u;
-        } else {
-          d = dplane + sp * pairw;
-          sp = (sp + 1u) & smask;
-          accumulate = fresh_left ? 0u : 1u;
-          fresh_left = fresh_left ? fresh_left - 1u : 0u;
-        }
-        if (PAIR)
-          ptx::mma2_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
-        else
-          ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t d, accumulate;
+      if (u16_is_ph(MODE)) {
+        d = dplane;
+        accumulate = (fresh_kb && tap == 0 && ks == 0) ? 0u : 1u;
+      } else if (MODE == U16_DECONV) {
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const uint32_t ph = (uint32_t)((kh == 1) * 2 + (kw == 1));
+        d = dplane + ph * pairw;
+        const bool first_tap = (tap == 0 || tap == 1 || tap == 3 || tap == 4);
+        accumulate = (fresh_kb && first_tap && ks == 0) ? 0u : 1u;
+      } else {
+        d = dplane + sp * pairw;
+        sp = (sp + 1u) & smask;
+        accumulate = fresh_left ? 0u : 1u;
+        fresh_left = fresh_left ? fresh_left - 1u : 0u;
       }
+      if (PAIR)
+        ptx::mma2_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
+      else
+        ptx::mma_f16_ss(d, u16_desc(ad + 2u * ks, a_hi32), u16_desc(bd + 2u * ks, w_hi32), idesc, accumulate);
     }
   }
+}
+
+template <int MODE, bool PAIR = false>
+__device__ __forceinline__ void u16_issue_plane(const U16Params& p, uint32_t abase, uint32_t wbase, uint32_t dplane,
+                                                uint32_t pairw, uint32_t idesc, uint32_t a_hi32, uint32_t w_hi32,
+                                                uint32_t tapw, int ksteps, uint32_t smask, uint32_t& sp, uint32_t& fresh_left,
+                                                bool fresh_kb) {
+  if (ksteps == 2)  // 32-channel K-blocks
+    u16_issue_plane_t<MODE, PAIR, 2>(p, abase, wbase, dplane, pairw, idesc, a_hi32, w_hi32, tapw, smask, sp, fresh_left, fresh_kb);
+  else if (ksteps == 4)  // 64-channel K-blocks
+    u16_issue_plane_t<MODE, PAIR, 4>(p, abase, wbase, dplane, pairw, idesc, a_hi32, w_hi32, tapw, smask, sp, fresh_left, fresh_kb);
+  else
+    u16_issue_plane_t<MODE, PAIR, 1>(p, abase, wbase, dplane, pairw, idesc, a_hi32, w_hi32, tapw, smask, sp, fresh_left, fresh_kb);
 }
 
 template <int MODE>
@@ -932,7 +945,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       if (ptx::elect_one()) ptx::mbar_arrive_leader(&bars->w_full);
       __syncwarp();
     }
-    uint32_t it = 0;
+    uint32_t s = 0, sph = 1;  // ring slot and the parity to wait for on its `empty` barrier
     for (long long tp = pair0; tp < num_pairs; tp += npairs) {
       long long tt = 2 * tp + rank;
       uint32_t tq, tx, ty, tn;
@@ -941,10 +954,11 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int n0 = (int)tn * p.bn;
       const int x0 = (int)tx * 8, y0 = (int)ty * p.bh;
       for (int kb = 0; kb < p.KB; ++kb) {
-        for (int plane = 0; plane < 2; ++plane, ++it) {
-          const int s = it % p.S;
-          ptx::mbar_wait(&bars->empty[s], ((it / p.S) & 1) ^ 1);
-          if (ptx::elect_one()) {
+        for (int plane = 0; plane < 2; ++plane) {
+          ptx::mbar_wait(&bars->empty[s], sph);
+          if (p.dbg & 2) {
+            if (leader && ptx::elect_one()) ptx::mbar_arrive(&bars->full[s]);
+          } else if (ptx::elect_one()) {
             const CUtensorMap* tm = plane ? &tm_lo : &tm_hi;
             uint8_t* dst = s_a + (size_t)s * p.slot_bytes;
             if (leader) ptx::mbar_expect_tx(&bars->full[s], 2u * p.box_bytes * (uint32_t)p.nbox);
@@ -956,6 +970,10 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             }
           }
           __syncwarp();
+          if (++s == (uint32_t)p.S) {
+            s = 0;
+            sph ^= 1u;
+          }
         }
       }
     }
@@ -971,7 +989,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const uint32_t pairw = 2u * (uint32_t)NPAD, smask = (uint32_t)p.nsplit - 1u;
       const int ksteps = p.ksteps;
       ptx::mbar_wait(&bars->w_full, 0);
-      uint32_t it = 0, ti = 0;
+      uint32_t ti = 0, s = 0, sph = 0;
       for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
         const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
         const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
@@ -979,11 +997,10 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         ptx::tc_fence_after();
         const uint32_t dbase = tmem_base + b * p.acc_cols;
         for (int kb = 0; kb < p.KB; ++kb) {
-          for (int plane = 0; plane < 2; ++plane, ++it) {
-            const int s = it % p.S;
-            ptx::mbar_wait(&bars->full[s], (it / p.S) & 1);
+          for (int plane = 0; plane < 2; ++plane) {
+            ptx::mbar_wait(&bars->full[s], sph);
             ptx::tc_fence_after();
-            if (ptx::elect_one()) {
+            if (!(p.dbg & 1) && ptx::elect_one()) {
               const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
               const uint32_t wbase = plane ? (ptx::smem_u32(s_wB + (size_t)kb * T * tapB) >> 4) | (1u << 16)
                                            : (ptx::smem_u32(s_wA + (size_t)kb * T * tapA) >> 4) | (1u << 16);
@@ -995,6 +1012,10 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             __syncwarp();
             if (ptx::elect_one()) ptx::tc_commit2(&bars->empty[s]);
             __syncwarp();
+            if (++s == (uint32_t)p.S) {
+              s = 0;
+              sph ^= 1u;
+            }
           }
         }
         if (ptx::elect_one()) ptx::tc_commit2(&bars->acc_full[b]);
@@ -1024,7 +1045,8 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int yt = (int)ty * p.bh + hh, xt = (int)tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
-      if (p.staged)
+      if (p.dbg & 4) {
+      } else if (p.staged)
         u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
                                        s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad);
       else
@@ -1218,6 +1240,13 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
     p.nsplit = 1;
     while (p.nsplit * 2 <= cap && p.nsplit < 4 && steps > 18 * p.nsplit) p.nsplit *= 2;
     p.acc_cols = (uint32_t)(p.nsplit * accw);
+  }
+  {
+    static const int dbg = [] {
+      const char* e = getenv("TIC_DBG");
+      return e ? atoi(e) : 0;
+    }();
+    p.dbg = dbg;
   }
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
   p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad) ? 1 : 0;

@@ -54,7 +54,7 @@ enum U16Mode : int { U16_S1 = 0, U16_S2 = 1, U16_DECONV = 2, U16_DECONV_PH = 3, 
 __host__ __device__ constexpr bool u16_is_ph(int mode) { return mode == U16_DECONV_PH || mode == U16_DECONV_RGB; }
 
 constexpr int kU16Threads = 384;
-constexpr int kU16MaxSlots = 6;
+constexpr int kU16MaxSlots = 8;
 
 struct U16Params {
   int mode;
@@ -71,7 +71,8 @@ struct U16Params {
   int cpad;              // PH: channels per phase column block (4 | 16 | 32)
   int oc0;               // first output channel of this launch (slice)
   int nsplit;            // conv: accumulator pairs the K steps rotate over; deconv: 1
-  int nbuf;              // TMEM tile buffers (1 | 2)
+  int nbuf;              // TMEM tile buffers (1 | 2 | 4): how far the MMAs run ahead of the epilogue
+  int nbshift;           // log2(nbuf)
   uint32_t acc_cols;     // TMEM columns per tile buffer
   uint32_t a_layout;     // descriptor layout code of the A rows (2 = SW128, 4 = SW64, 6 = SW32)
   uint32_t w_layout;     // ... of the weight rows
@@ -236,7 +237,7 @@ __global__ void u16_split_symlut_kernel(const uint8_t* __restrict__ sym, const f
 struct U16SmemBars {
   uint64_t w_full;
   uint64_t full[kU16MaxSlots], empty[kU16MaxSlots];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[4], acc_empty[4];
   uint32_t tmem_base;
 };
 
@@ -724,7 +725,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       ptx::mbar_init(&bars->full[i], 1);
       ptx::mbar_init(&bars->empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
       ptx::mbar_init(&bars->acc_empty[i], p.staged ? 4 : 8);
     }
@@ -792,8 +793,8 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     ptx::mbar_wait(&bars->w_full, 0);
     uint32_t it = 0, ti = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
-      const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
-      const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+      const uint32_t b = ti & ((uint32_t)p.nbuf - 1u);
+      const uint32_t use = ti >> p.nbshift;
       ptx::mbar_wait(&bars->acc_empty[b], (use & 1) ^ 1);
       ptx::tc_fence_after();
       const uint32_t dbase = tmem_base + b * p.acc_cols;
@@ -828,8 +829,8 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint32_t ti = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
       if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
-      const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
-      const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+      const uint32_t b = ti & ((uint32_t)p.nbuf - 1u);
+      const uint32_t use = ti >> p.nbshift;
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
       ptx::tc_fence_after();
       long long tt = tile;
@@ -881,7 +882,9 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 // weight tile (leader W_hi, peer W_lo' for the stacked product; a half of W_hi each for A_lo' x W_hi).
 // Barriers: `full` lives in the leader and counts the bytes of both CTAs' boxes; `empty` and `acc_full` are
 // committed to both CTAs (multicast); `acc_empty` lives in the leader and collects both epilogues.
-template <int MODE>
+// PPS = planes per ring slot (compile-time: the issuing warp's instruction stream bounds the layers with small N, and
+// any run-time structure in it — loops, branches, calls — measured 5-25 % slower on those layers).
+template <int MODE, int PPS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kU16Threads, 1)
 u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const U16Params p,
                 const LayerArgs a) {
@@ -907,7 +910,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       ptx::mbar_init(&bars->full[i], 1);
       ptx::mbar_init(&bars->empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
       ptx::mbar_init(&bars->acc_empty[i], p.staged ? 8 : 16);  // epilogue warps of both CTAs (leader's copy is the live one)
     }
@@ -925,6 +928,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   const uint32_t tmem_base = bars->tmem_base;
   const long long npairs = gridDim.x >> 1, pair0 = blockIdx.x >> 1;
   const long long num_pairs = (p.num_tiles + 1) >> 1;
+  const uint32_t SR = (uint32_t)p.S / (uint32_t)PPS;   // ring slots
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own weight halves once, then per tile and K-block the two planes =====
@@ -953,24 +957,33 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       fast_divmod(tq, p.ty_d, tn, ty);
       const int n0 = (int)tn * p.bn;
       const int x0 = (int)tx * 8, y0 = (int)ty * p.bh;
+      // one ring slot = the hi AND the lo' box of a K-block (one barrier round trip per K-block, not per plane: the
+      // fixed cost of a wait / commit pair in the single issuing warp is ~350 cycles, TIC_DBG=7)
+      // one ring slot = PPS planes of a K-block: the hi AND the lo' box when four plane buffers fit (one barrier round
+      // trip per K-block, not per plane: the fixed cost of a wait / commit pair in the single issuing warp is ~350
+      // cycles, TIC_DBG=7), else one plane
       for (int kb = 0; kb < p.KB; ++kb) {
-        for (int plane = 0; plane < 2; ++plane) {
+#pragma unroll
+        for (int pl0 = 0; pl0 < 2; pl0 += PPS) {
           ptx::mbar_wait(&bars->empty[s], sph);
           if (p.dbg & 2) {
             if (leader && ptx::elect_one()) ptx::mbar_arrive(&bars->full[s]);
           } else if (ptx::elect_one()) {
-            const CUtensorMap* tm = plane ? &tm_lo : &tm_hi;
-            uint8_t* dst = s_a + (size_t)s * p.slot_bytes;
-            if (leader) ptx::mbar_expect_tx(&bars->full[s], 2u * p.box_bytes * (uint32_t)p.nbox);
-            if (MODE == U16_S2) {
-              ptx::tma2_load_5d(dst, tm, &bars->full[s], kb * p.kc, x0, 0, n0, y0);
-              if (p.nbox == 2) ptx::tma2_load_5d(dst + p.box_stride, tm, &bars->full[s], a.cin + kb * p.kc, x0, 0, n0, y0);
-            } else {
-              ptx::tma2_load_4d(dst, tm, &bars->full[s], kb * p.kc, x0 - 1, n0, y0 - 1);
+            if (leader) ptx::mbar_expect_tx(&bars->full[s], (uint32_t)PPS * 2u * p.box_bytes * (uint32_t)p.nbox);
+#pragma unroll
+            for (int q = 0; q < PPS; ++q) {
+              const CUtensorMap* tm = (pl0 + q) ? &tm_lo : &tm_hi;
+              uint8_t* dst = s_a + (size_t)((uint32_t)PPS * s + (uint32_t)q) * p.slot_bytes;
+              if (MODE == U16_S2) {
+                ptx::tma2_load_5d(dst, tm, &bars->full[s], kb * p.kc, x0, 0, n0, y0);
+                if (p.nbox == 2) ptx::tma2_load_5d(dst + p.box_stride, tm, &bars->full[s], a.cin + kb * p.kc, x0, 0, n0, y0);
+              } else {
+                ptx::tma2_load_4d(dst, tm, &bars->full[s], kb * p.kc, x0 - 1, n0, y0 - 1);
+              }
             }
           }
           __syncwarp();
-          if (++s == (uint32_t)p.S) {
+          if (++s == SR) {
             s = 0;
             sph ^= 1u;
           }
@@ -991,28 +1004,34 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       ptx::mbar_wait(&bars->w_full, 0);
       uint32_t ti = 0, s = 0, sph = 0;
       for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
-        const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
-        const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+        const uint32_t b = ti & ((uint32_t)p.nbuf - 1u);
+        const uint32_t use = ti >> p.nbshift;
         ptx::mbar_wait(&bars->acc_empty[b], (use & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t dbase = tmem_base + b * p.acc_cols;
         for (int kb = 0; kb < p.KB; ++kb) {
-          for (int plane = 0; plane < 2; ++plane) {
+#pragma unroll
+          for (int pl0 = 0; pl0 < 2; pl0 += PPS) {
             ptx::mbar_wait(&bars->full[s], sph);
             ptx::tc_fence_after();
             if (!(p.dbg & 1) && ptx::elect_one()) {
-              const uint32_t abase = (ptx::smem_u32(s_a + (size_t)s * p.slot_bytes) >> 4) | (1u << 16);
-              const uint32_t wbase = plane ? (ptx::smem_u32(s_wB + (size_t)kb * T * tapB) >> 4) | (1u << 16)
-                                           : (ptx::smem_u32(s_wA + (size_t)kb * T * tapA) >> 4) | (1u << 16);
-              uint32_t sp = 0, fresh_left = (plane == 0 && kb == 0) ? (uint32_t)p.nsplit : 0u;
-              u16_issue_plane<MODE, true>(p, abase, wbase, dbase + (plane ? (uint32_t)NPAD : 0u), pairw,
-                                          plane ? idesc_lo : idesc_st, a_hi32, w_hi32, (plane ? tapB : tapA) >> 4, ksteps, smask,
-                                          sp, fresh_left, plane == 0 && kb == 0);
+#pragma unroll
+              for (int q = 0; q < PPS; ++q) {
+                const int plane = pl0 + q;
+                const uint32_t abase =
+                    (ptx::smem_u32(s_a + (size_t)((uint32_t)PPS * s + (uint32_t)q) * p.slot_bytes) >> 4) | (1u << 16);
+                const uint32_t wbase = plane ? (ptx::smem_u32(s_wB + (size_t)kb * T * tapB) >> 4) | (1u << 16)
+                                             : (ptx::smem_u32(s_wA + (size_t)kb * T * tapA) >> 4) | (1u << 16);
+                uint32_t sp = 0, fresh_left = (plane == 0 && kb == 0) ? (uint32_t)p.nsplit : 0u;
+                u16_issue_plane<MODE, true>(p, abase, wbase, dbase + (plane ? (uint32_t)NPAD : 0u), pairw,
+                                            plane ? idesc_lo : idesc_st, a_hi32, w_hi32, (plane ? tapB : tapA) >> 4, ksteps, smask,
+                                            sp, fresh_left, plane == 0 && kb == 0);
+              }
             }
             __syncwarp();
             if (ptx::elect_one()) ptx::tc_commit2(&bars->empty[s]);
             __syncwarp();
-            if (++s == (uint32_t)p.S) {
+            if (++s == SR) {
               s = 0;
               sph ^= 1u;
             }
@@ -1033,8 +1052,8 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint32_t ti = 0;
     for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
       if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
-      const uint32_t b = p.nbuf == 2 ? (ti & 1u) : 0u;
-      const uint32_t use = p.nbuf == 2 ? (ti >> 1) : ti;
+      const uint32_t b = ti & ((uint32_t)p.nbuf - 1u);
+      const uint32_t use = ti >> p.nbshift;
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
       ptx::tc_fence_after();
       long long tt = 2 * tp + rank;
@@ -1114,10 +1133,10 @@ inline cudaError_t u16_launch_t(cudaStream_t stream, const CUtensorMap& th, cons
   return cudaGetLastError();
 }
 
-template <int MODE>
-inline cudaError_t u16_launch_pair_t(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
-                                     const LayerArgs& a, int grid, size_t smem) {
-  auto k = u16_pair_kernel<MODE>;
+template <int MODE, int PPS>
+inline cudaError_t u16_launch_pair_pps(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
+                                       const LayerArgs& a, int grid, size_t smem) {
+  auto k = u16_pair_kernel<MODE, PPS>;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1126,6 +1145,13 @@ inline cudaError_t u16_launch_pair_t(cudaStream_t stream, const CUtensorMap& th,
   }
   k<<<grid, kU16Threads, smem, stream>>>(th, tl, p, a);  // __cluster_dims__(2, 1, 1): grid is even
   return cudaGetLastError();
+}
+template <int MODE>
+inline cudaError_t u16_launch_pair_t(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
+                                     const LayerArgs& a, int grid, size_t smem) {
+  // both planes of a K-block share a ring slot when four plane buffers fit
+  return p.S >= 4 ? u16_launch_pair_pps<MODE, 2>(stream, th, tl, p, a, grid, smem)
+                  : u16_launch_pair_pps<MODE, 1>(stream, th, tl, p, a, grid, smem);
 }
 
 struct U16Plan {
@@ -1224,7 +1250,7 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   if (p.mode == U16_DECONV_PH) {
     p.nsplit = 1;
     p.acc_cols = (uint32_t)accw;
-    p.nbuf = 2;
+    p.nbuf = accw * 4 <= 512 ? 4 : 2;
   } else if (p.mode == U16_DECONV) {
     p.nsplit = 1;
     p.acc_cols = 4u * accw;
@@ -1240,7 +1266,18 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
     p.nsplit = 1;
     while (p.nsplit * 2 <= cap && p.nsplit < 4 && steps > 18 * p.nsplit) p.nsplit *= 2;
     p.acc_cols = (uint32_t)(p.nsplit * accw);
+    if (p.acc_cols * 4 <= 512) p.nbuf = 4;
   }
+  // The accumulator hand-over (tcgen05.commit -> epilogue wake-up -> cross-CTA arrive -> issuer wake-up) is ~1400
+  // cycles; with two buffers that alone is ~700 cycles per tile (TIC_DBG=7 skeleton: 0.96 of decode_0's 1.95 ms).
+  {
+    static const int maxbuf = [] {
+      const char* e = getenv("TIC_MAX_NBUF");
+      return e ? atoi(e) : 4;
+    }();
+    while (p.nbuf > maxbuf && p.nbuf > 1) p.nbuf /= 2;
+  }
+  p.nbshift = p.nbuf == 4 ? 2 : (p.nbuf == 2 ? 1 : 0);
   {
     static const int dbg = [] {
       const char* e = getenv("TIC_DBG");
@@ -1254,6 +1291,7 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   const size_t wres = ((p.w_bytes + 1023u) & ~1023u) + (p.staged ? kU16StageBytes : 0u);
   if (wres + 2 * (size_t)p.slot_bytes > budget) return false;
   p.S = (int)std::min<size_t>(kU16MaxSlots, (budget - wres) / p.slot_bytes);
+  if (pair && p.S >= 4) p.S &= ~1;  // the pair kernel's ring slots hold both planes when four plane buffers fit
   out->cs = cs;
   out->p = p;
   out->smem = wres + (size_t)p.S * p.slot_bytes + sizeof(U16SmemBars) + 1024;

@@ -30,6 +30,7 @@ struct F16Params {
   int npad;
   int nbuf;              // TMEM tile buffers (power of two, <= 4)
   const uint8_t* wimg;   // [W_hi npad rows ; W_lo' npad rows] x 64 B, SW64
+  int dbg;               // measurement aid (env TIC_DBG, stride-2 kernel): 1 = no MMA issue, 2 = builders only arrive, 4 = no epilogue work
 };
 
 struct F16SmemBars {
@@ -242,10 +243,11 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
       fast_divmod(tq, p.ty_d, tn, ty);
       const int n = (int)tn * p.bn + nb;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
-      if (staged)
+      if (staged) {
         u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * p.bh + hh, (int)tx * 8 + xx, n < p.n, s_bias,
-                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0);
-      else
+                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0, &bars->acc_empty[b], 1);
+        continue;  // the staged epilogue released the buffer itself
+      } else
         u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * p.bh + hh, (int)tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
                                   h_valid);
       ptx::tc_fence_before();
@@ -424,6 +426,14 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
     if ((long long)blockIdx.x < p.num_tiles) request(blockIdx.x, raw, okm);
     if ((long long)blockIdx.x + gridDim.x < p.num_tiles) request(blockIdx.x + gridDim.x, raw_b, okm_b);
     uint32_t it = 0;
+    if (p.dbg & 2) {
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int s = it % kW2Stages;
+        ptx::mbar_wait(&bars->empty[s], ((it / kW2Stages) & 1) ^ 1);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
+      }
+    } else
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       uint32_t raw_n[9];
       unsigned okm_n = 0;
@@ -490,7 +500,7 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
       ptx::mbar_wait(&bars->acc_empty[b], ((it >> nbshift) & 1) ^ 1);
       ptx::mbar_wait(&bars->full[s], (it / kW2Stages) & 1);
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
+      if (!(p.dbg & 1) && ptx::elect_one()) {
         const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * 10240) >> 4) | a_lbo;
         const uint32_t al = ah + (kW2Plane >> 4);
         const uint32_t d = tmem_base + b * pairw;
@@ -526,10 +536,12 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
       fast_divmod(tq, p.ty_d, tn, ty);
       const int n = (int)tn;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
-      if (staged)
+      if (p.dbg & 4) {
+      } else if (staged) {
         u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, s_bias,
-                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0);
-      else
+                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0, &bars->acc_empty[b], 1);
+        continue;  // the staged epilogue released the buffer itself
+      } else
         u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
       ptx::tc_fence_before();
       __syncwarp();
@@ -599,6 +611,13 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   p.ty_d = make_fastdiv((uint32_t)p.tiles_y);
   p.txy_d = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
   p.npad = a.cout;
+  {
+    static const int dbg = [] {
+      const char* e = getenv("TIC_DBG");
+      return e ? atoi(e) : 0;
+    }();
+    p.dbg = dbg;
+  }
   p.nbuf = std::min(4, 512 / (2 * p.npad));
   const bool windowed = stride == 2 && p.bn == 1;  // operands straight from the staged input tile (no im2col)
   if (!fw->img || fw->windowed != windowed) {

@@ -543,7 +543,8 @@ template <int MODE, int CEND>
 __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
                                                            const uint32_t tbuf, const int n, const int yt, const int xt,
                                                            const bool valid, const float* s_bias, const uint32_t stage,
-                                                           const int lane, const int cpad) {
+                                                           const int lane, const int cpad, uint64_t* rel_bar,
+                                                           const int rel_kind) {
   constexpr bool kPh = u16_is_ph(MODE);
   constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane: 2 | 4 | 8
   constexpr int MSH = M == 2 ? 1 : (M == 4 ? 2 : 3);
@@ -573,6 +574,19 @@ __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, c
         const int c = ci * 16;
         float v[16];
         u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
+        if (px == NPX - 1 && ci == NCI - 1 && py == (kPh ? 1 : 0)) {
+          // last TMEM read of this tile: hand the accumulator buffer back before the remaining math and stores, so the
+          // MMAs of the tile after next overlap them (with two buffers the hand-over latency was serialised: decode_1
+          // ran at epilogue + MMA time per tile)
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rel_kind == 2)
+              ptx::mbar_arrive_leader(rel_bar);
+            else
+              ptx::mbar_arrive(rel_bar);
+          }
+        }
         const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -641,14 +655,16 @@ template <int MODE>
 __device__ __forceinline__ void u16_epilogue_tile_staged(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
                                                          const uint32_t tbuf, const int n, const int yt, const int xt,
                                                          const bool valid, const float* s_bias, uint8_t* stage, const int lane,
-                                                         const int cpad) {
+                                                         const int cpad, uint64_t* rel_bar, const int rel_kind) {
+  // rel_bar: the tile buffer's `acc_empty` barrier, arrived on (rel_kind 1: this CTA's, 2: the pair leader's) by lane 0
+  // right after the tile's last TMEM read
   if (MODE == U16_DECONV_RGB) return;
   const int cend = u16_is_ph(MODE) ? cpad : NPAD;
   const uint32_t st = ptx::smem_u32(stage);
   if (cend == 32)
-    u16_epilogue_tile_staged_t<MODE, 32>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad);
+    u16_epilogue_tile_staged_t<MODE, 32>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind);
   else if (cend == 16)
-    u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad);
+    u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind);
 }
 
 // KS = MMAs (K = 16) per tap and K-block, compile-time: with a run-time bound the unrolled body carries four
@@ -841,11 +857,12 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int yt = (int)ty * p.bh + hh, xt = (int)tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
-      if (p.staged)
+      if (p.staged) {
         u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
-                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad);
-      else
-        u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
+                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 1);
+        continue;  // the staged epilogue released the buffer itself
+      }
+      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
@@ -1065,10 +1082,11 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
       if (p.dbg & 4) {
-      } else if (p.staged)
+      } else if (p.staged) {
         u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
-                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad);
-      else
+                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 2);
+        continue;  // the staged epilogue released the buffer itself
+      } else
         u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();

@@ -30,6 +30,7 @@ struct F16Params {
   int npad;
   int nbuf;              // TMEM tile buffers (power of two, <= 4)
   const uint8_t* wimg;   // [W_hi npad rows ; W_lo' npad rows] x 64 B, SW64
+  int use_tma;           // stride-2 kernel: raw u8 windows arrive by TMA (image geometry allows it, f16_first_tma_ok)
   int dbg;               // measurement aid (env TIC_DBG, stride-2 kernel): 1 = no MMA issue, 2 = builders only arrive, 4 = no epilogue work
 };
 
@@ -290,7 +291,15 @@ constexpr int kW2Rows = 33;                       // 2 * 16 + 1
 constexpr uint32_t kW2Plane = 4864;               // >= 33 * 144, multiple of 128
 constexpr uint32_t kW2Stage = 2 * kW2Plane + 512; // hi | lo', 1024-aligned below
 constexpr int kW2Stages = 4;
-constexpr int kW2Threads = 544;                   // warps 0-7 builders, 8-15 epilogue, 16 MMA + TMEM
+constexpr int kW2Threads = 576;                   // warps 0-7 builders, 8-15 epilogue, 16 MMA + TMEM, 17 raw-window TMA
+// TMA-fed builders (u8 images whose patch grid needs no reflect padding and whose row pitch is a multiple of 16
+// bytes): warp 17 fetches the raw 33-row x 54-byte window of a tile as a 33 x 64-byte box (3-D map over
+// [B, H, W * 3] bytes; rows below the image come back as zeros), kRawStages tiles ahead.  A builder thread then owns
+// 4 consecutive pixels of a row = three aligned words of shared memory: no per-thread image addressing, no global
+// load latency held in registers (the gather path kept 27 raw values of three tiles live), 165 busy threads.
+constexpr int kRawStages = 6;
+constexpr uint32_t kRawRow = 64;
+constexpr uint32_t kRawStage = 2176;              // 33 * 64 = 2112, padded to a multiple of 128
 
 // device [9][3][cout] fp32 -> per kh: [k group (2)][row (2 npad: hi, lo')][8 halves], k = px * 4 + c
 __global__ void f16_build_weights_s2_kernel(const float* __restrict__ w, int cout, int npad, uint8_t* __restrict__ img) {
@@ -309,17 +318,20 @@ __global__ void f16_build_weights_s2_kernel(const float* __restrict__ w, int cou
 struct W2SmemBars {
   uint64_t full[kW2Stages], empty[kW2Stages];
   uint64_t acc_full[4], acc_empty[4];
+  uint64_t raw_full[kRawStages], raw_empty[kRawStages];
   uint32_t tmem_base;
 };
 
-__global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Params p, const LayerArgs a) {
+__global__ void __launch_bounds__(kW2Threads, 1)
+f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params p, const LayerArgs a) {
   const int NPAD = p.npad;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;                                  // kW2Stages stages of kW2Stage bytes
   uint8_t* s_w = smem + kW2Stages * 10240;              // 192 * npad bytes
   uint8_t* s_stage = s_w + 192 * 64;                    // 8 x 4 KB epilogue stages
-  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_stage + kU16StageBytes);
+  uint8_t* s_rawwin = s_stage + kU16StageBytes;         // kRawStages raw windows (TMA destination, 128-byte aligned)
+  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_rawwin + kRawStages * kRawStage);
   const bool staged = u16_staged_ok(a, U16_S1, p.nbuf, p.npad);
   __shared__ unsigned s_hist[256];
   __shared__ __align__(16) float s_bias[128];
@@ -346,6 +358,10 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
       ptx::mbar_init(&bars->acc_full[i], 1);
       ptx::mbar_init(&bars->acc_empty[i], staged ? 4 : 8);
     }
+    for (int i = 0; i < kRawStages; ++i) {
+      ptx::mbar_init(&bars->raw_full[i], 1);
+      ptx::mbar_init(&bars->raw_empty[i], 8);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 16) {
@@ -362,7 +378,90 @@ __global__ void __launch_bounds__(kW2Threads, 1) f16_first_s2_kernel(const F16Pa
   int nbshift = 0;
   while ((1 << nbshift) < p.nbuf) ++nbshift;
 
-  if (warp < 8) {
+  if (warp < 8 && p.use_tma) {
+    // ===== builders, TMA-fed: thread = (row, quad of 4 pixels); 33 x 5 = 165 threads; quad 4 holds pixels 16, 17 =====
+    const int ry = tid / 5, qx = tid - ry * 5;
+    const bool live = ry < kW2Rows;
+    const uint32_t my_raw = (uint32_t)ry * kRawRow + (uint32_t)qx * 12u;
+    const uint32_t my_dst = (uint32_t)(ry * kW2Cols + 4 * qx) * 8u;
+    const int npx = qx == 4 ? 2 : 4;   // pixels of this quad inside the 18-column window
+    uint32_t it = 0, r = 0, rph = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      // window origin inside the patch: SAME padding (0, 1) = zeros at row / column P
+      unsigned n, rt, ty, tx;
+      fast_divmod((unsigned)tile, p.txy_d, n, rt);
+      fast_divmod(rt, p.tx_d, ty, tx);
+      const int iy = 32 * (int)ty + ry, ix = 16 * (int)tx + 4 * qx;
+      ptx::mbar_wait(&bars->raw_full[r], rph);
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+      if (live) {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(s_rawwin + (size_t)r * kRawStage + my_raw);
+        w0 = rp[0];
+        w1 = rp[1];
+        w2 = rp[2];
+      }
+      uint2 vh[4], vl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // pixel j = bytes 3j .. 3j+2 of the 12
+        const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
+        const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
+        const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
+        const bool okj = live && iy < p.P && ix + j < p.P;
+        const uint32_t x0 = okj ? s_plut[b0] : 0u;
+        const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
+        const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
+        vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
+        vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->raw_empty[r]);   // the window's words are in registers (used above)
+      if (++r == kRawStages) {
+        r = 0;
+        rph ^= 1u;
+      }
+      const int s = it % kW2Stages;
+      ptx::mbar_wait(&bars->empty[s], ((it / kW2Stages) & 1) ^ 1);
+      if (live) {
+        uint8_t* st = s_a + (size_t)s * 10240 + my_dst;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < npx) {
+            *reinterpret_cast<uint2*>(st + j * 8) = vh[j];
+            *reinterpret_cast<uint2*>(st + kW2Plane + j * 8) = vl[j];
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
+    }
+  } else if (warp == 17) {
+    // ===== raw-window producer: one 33 x 64-byte box per tile, kRawStages tiles ahead of the builders =====
+    if (p.use_tma) {
+      const Geo g = a.geo;
+      if (ptx::elect_one()) ptx::prefetch_tmap(&tm_img);
+      __syncwarp();
+      uint32_t r = 0, rph = 1;
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&bars->raw_empty[r], rph);
+        if (ptx::elect_one()) {
+          unsigned n, rt, ty, tx, img, gy, gx;
+          fast_divmod((unsigned)tile, p.txy_d, n, rt);
+          fast_divmod(rt, p.tx_d, ty, tx);
+          geo_decode(g, (unsigned)g.n0 + n, img, gy, gx);
+          const int Yb = (int)gy * g.P + 32 * (int)ty, Xb = (int)gx * g.P + 16 * (int)tx;
+          ptx::mbar_expect_tx(&bars->raw_full[r], kW2Rows * kRawRow);
+          ptx::tma_load_3d(s_rawwin + (size_t)r * kRawStage, &tm_img, &bars->raw_full[r], Xb * 3, Yb, (int)img);
+        }
+        __syncwarp();
+        if (++r == kRawStages) {
+          r = 0;
+          rph ^= 1u;
+        }
+      }
+    }
+  } else if (warp < 8) {
     // ===== builders: 198 threads stage the 33 x 18 input pixels of a tile, 3 consecutive pixels (9 bytes)
     // per thread.  The gather is latency-bound, so the raw bytes of tile i+1 are requested before tile i is
     // converted; tiles whose window lies inside the image skip the reflect arithmetic. =====
@@ -581,6 +680,17 @@ inline bool f16_first_supported(const LayerArgs& a, int kind, int stride) {
   return true;
 }
 
+// The raw-window TMA path needs: u8 pixels, a patch grid that covers the image exactly (no reflect padding, no grid
+// offset), and a global address / row pitch the tensor map accepts (16-byte multiples).
+inline bool f16_first_tma_ok(const LayerArgs& a) {
+  const Geo& g = a.geo;
+  if (a.in_mode != IO_U8_NORM) return false;
+  if (g.oy != 0 || g.ox != 0 || g.H != g.gh * g.P || g.W != g.gw * g.P || g.P != a.hin) return false;
+  if ((g.W * 3) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15u) != 0) return false;
+  if (a.hin % 32 != 0) return false;
+  return true;
+}
+
 struct F16Weights {
   uint8_t* img = nullptr;
   bool windowed = false;
@@ -633,7 +743,26 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   }
   p.wimg = fw->img;
   const size_t smem = kF16Stages * kF16StageBytes + 2 * 64 * 64 + kU16StageBytes + sizeof(F16SmemBars) + 1024;
-  const size_t smem_w2 = kW2Stages * 10240 + 192 * 64 + kU16StageBytes + sizeof(W2SmemBars) + 1024;
+  const size_t smem_w2 = kW2Stages * 10240 + 192 * 64 + kU16StageBytes + kRawStages * kRawStage + sizeof(W2SmemBars) + 1024;
+  CUtensorMap tm_img{};
+  p.use_tma = 0;
+  if (windowed && f16_first_tma_ok(a)) {
+    static const bool off = getenv("TIC_FIRST_NO_TMA") != nullptr;
+    auto encode = umma_encode_fn();
+    if (!off && encode) {
+      const Geo& g = a.geo;
+      const long long per_img = (long long)g.gh * g.gw;
+      const cuuint64_t nimg = (cuuint64_t)((g.n0 + a.n + per_img - 1) / per_img);
+      cuuint64_t dims[3] = {(cuuint64_t)g.W * 3, (cuuint64_t)g.H, nimg};
+      cuuint64_t strides[2] = {(cuuint64_t)g.W * 3, (cuuint64_t)g.H * g.W * 3};
+      cuuint32_t box[3] = {kRawRow, (cuuint32_t)kW2Rows, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      CUresult r = encode(&tm_img, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(a.in), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) p.use_tma = 1;
+    }
+  }
   const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
   static bool configured = false;
   if (!configured) {
@@ -644,7 +773,7 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
     configured = true;
   }
   if (windowed)
-    f16_first_s2_kernel<<<grid, kW2Threads, smem_w2, stream>>>(p, a);
+    f16_first_s2_kernel<<<grid, kW2Threads, smem_w2, stream>>>(tm_img, p, a);
   else if (stride == 1)
     f16_first_kernel<1><<<grid, kF16Threads, smem, stream>>>(p, a);
   else

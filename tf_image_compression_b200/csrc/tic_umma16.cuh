@@ -322,6 +322,25 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
       const int Y = g.oy + (int)gy * g.P + 2 * yt + half, X = g.ox + (int)gx * g.P + 2 * xt;
       if (Y >= g.H) return;
       const long long off = (((long long)img * g.H + Y) * g.W + X) * 3;
+      if (a.out_mode == IO_DENORM_U8 && X + 1 < g.W && !(off & 1)) {
+        // both pixels inside the image and 2-byte aligned (X is even: any even W): three 2-byte stores instead of six bytes
+        uint32_t q[6];
+#pragma unroll
+        for (int px = 0; px < 2; ++px)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float m = half ? v[8 + px * 4 + c] : v[px * 4 + c];
+            const float l = half ? u[8 + px * 4 + c] : u[px * 4 + c];
+            float y = apply_act(__fadd_rn(__fmaf_rn(l, 1.0f / 2048.0f, m), s_bias[c]), a.act);
+            y = tic_denorm_clip(y, a.mean[c], a.stdv[c]);
+            q[px * 3 + c] = (uint32_t)(int)rintf(y);
+          }
+        unsigned short* o2 = reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(a.out) + off);
+        o2[0] = (unsigned short)(q[0] | (q[1] << 8));
+        o2[1] = (unsigned short)(q[2] | (q[3] << 8));
+        o2[2] = (unsigned short)(q[4] | (q[5] << 8));
+        return;
+      }
 #pragma unroll
       for (int px = 0; px < 2; ++px) {
         if (X + px >= g.W) break;
@@ -569,12 +588,30 @@ __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, c
       const int spix = kPh ? ((lane >> 3) * 16 + 2 * (lane & 7) + px) : lane;   // pixel slot in the stage
       const uint32_t sp = stage + (uint32_t)spix * (M * 16);
       const int sw = (spix >> FSH) & (M - 1);
+      // all TMEM reads of this pixel first (one wait for its NCI chunks), then the math
+      float vv[NCI][16];
+      if (kPh || MODE == U16_DECONV || nsplit == 1) {
+        float uu[NCI][16];
+#pragma unroll
+        for (int ci = 0; ci < NCI; ++ci) {
+          const uint32_t t0 = tbuf + (kPh ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + ci * 16;
+          ptx::tmem_ld16_nowait(t0 + NPAD, uu[ci]);
+          ptx::tmem_ld16_nowait(t0, vv[ci]);
+        }
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int ci = 0; ci < NCI; ++ci)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) vv[ci][i] = __fmaf_rn(uu[ci][i], 1.0f / 2048.0f, vv[ci][i]);
+      } else {
+#pragma unroll
+        for (int ci = 0; ci < NCI; ++ci) u16_load_chunk<MODE>(vv[ci], tbuf, NPAD, nsplit, ph, ci * 16, cpad);
+      }
 #pragma unroll
       for (int ci = 0; ci < NCI; ++ci) {
         const int c = ci * 16;
-        float v[16];
-        u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
-        if (px == NPX - 1 && ci == NCI - 1 && py == (kPh ? 1 : 0)) {
+        float(&v)[16] = vv[ci];
+        if (px == NPX - 1 && ci == 0 && py == (kPh ? 1 : 0)) {
           // last TMEM read of this tile: hand the accumulator buffer back before the remaining math and stores, so the
           // MMAs of the tile after next overlap them (with two buffers the hand-over latency was serialised: decode_1
           // ran at epilogue + MMA time per tile)

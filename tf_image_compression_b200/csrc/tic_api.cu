@@ -550,21 +550,49 @@ int patches_per_chunk(const tic_codec* h, int P) {
   return std::max(1, c);
 }
 
-// Host-staged calls overlap H2D, kernels and D2H chunk by chunk; what does not overlap is the first chunk's H2D
-// and the last chunk's kernels + D2H, so chunks are equal-sized and small: `host_chunks` (16; measured 8 / 12 / 16 /
-// 24 chunks -> 12.8 / 12.9 / 13.2 / 13.1 Gpixel/s on the 64-image round trip) as long as a chunk keeps >= 768
-// patches of 128x128 (enough tiles to fill 148 SMs in every layer).
-int64_t host_units_per_chunk(int64_t units, int64_t upc, double patches128_per_unit) {
+// Host-staged calls overlap H2D, kernels and D2H chunk by chunk; what does not overlap is the first chunk's H2D and
+// the last chunk's kernels + D2H, so chunks are equal-sized and small: 16 of them as long as a chunk keeps >= 768
+// patches of 128x128 (measured on the 64-image round trip: 8 / 12 / 16 / 24 chunks -> 12.8 / 12.9 / 13.2 / 13.1
+// Gpixel/s).  A ramped schedule (chunks doubling from 384 patches to the workspace chunk and halving again:
+// 2, 4, 8, 18, 18, 8, 4, 2 images) was measured SLOWER (11.3 Gpixel/s): the round trip is bound by the D2H direction
+// running next to the H2D (654 MB at ~45 GB/s under duplex load), and large chunks leave it idle at both ends.
+// TIC_HOST_RAMP=1 selects the ramp, TIC_HOST_CHUNKS the equal-chunk count.
+std::vector<int64_t> host_chunk_schedule(int64_t units, int64_t cap, double patches128_per_unit) {
+  static const bool ramp = getenv("TIC_HOST_RAMP") != nullptr;
   static const int want = [] {
     const char* e = getenv("TIC_HOST_CHUNKS");
     const int v = e ? atoi(e) : 16;
     return v < 1 ? 1 : v;
   }();
-  int64_t chunks = (units + upc - 1) / upc;
-  const int64_t by_size = (int64_t)((double)units * patches128_per_unit / 768.0);
-  chunks = std::max<int64_t>(chunks, std::min<int64_t>(want, by_size));
-  chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, units));
-  return (units + chunks - 1) / chunks;
+  cap = std::max<int64_t>(1, std::min(cap, units));
+  std::vector<int64_t> out;
+  if (!ramp) {
+    int64_t chunks = (units + cap - 1) / cap;
+    const int64_t by_size = (int64_t)((double)units * patches128_per_unit / 768.0);
+    chunks = std::max<int64_t>(chunks, std::min<int64_t>(want, by_size));
+    chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, units));
+    const int64_t upc = (units + chunks - 1) / chunks;
+    for (int64_t u0 = 0; u0 < units; u0 += upc) out.push_back(std::min<int64_t>(upc, units - u0));
+    return out;
+  }
+  std::vector<int64_t> up;
+  int64_t ramp_units = 0;
+  int64_t v = std::max<int64_t>(1, (int64_t)(384.0 / std::max(patches128_per_unit, 1e-9) + 0.999));
+  while (v < cap && 2 * (ramp_units + v) <= units / 2) {
+    up.push_back(v);
+    ramp_units += v;
+    v *= 2;
+  }
+  out = up;
+  const int64_t rem = units - 2 * ramp_units;
+  const int64_t nmid = (rem + cap - 1) / cap;
+  for (int64_t i = 0, left = rem; i < nmid; ++i) {
+    const int64_t c = (left + (nmid - i) - 1) / (nmid - i);
+    out.push_back(c);
+    left -= c;
+  }
+  for (auto it = up.rbegin(); it != up.rend(); ++it) out.push_back(*it);
+  return out;
 }
 
 // Generic chunked driver.  `units` are processed `upc` (units per chunk) at a time; a unit is a
@@ -588,7 +616,8 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
     return TIC_OK;
   }
   // host buffers: double-buffered staging, copies on side streams
-  upc = host_units_per_chunk(units, upc, patches128_per_unit);
+  const std::vector<int64_t> sched = host_chunk_schedule(units, upc, patches128_per_unit);
+  upc = *std::max_element(sched.begin(), sched.end());
   const size_t in_need = (size_t)upc * in_unit_bytes, out_need = (size_t)upc * out_unit_bytes;
   if (h->stage_in_bytes < in_need) {
     for (int b = 0; b < 2; ++b) {
@@ -608,10 +637,10 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
     for (int b = 0; b < 2; ++b) TIC_CUDA(h, cudaMalloc(&h->stage_out[b], out_need));
     h->stage_out_bytes = out_need;
   }
-  int64_t idx = 0;
-  for (int64_t u0 = 0; u0 < units; u0 += upc, ++idx) {
+  int64_t u0 = 0;
+  for (int64_t idx = 0; idx < (int64_t)sched.size(); u0 += sched[idx], ++idx) {
     const int b = (int)(idx & 1);
-    int64_t nu = std::min<int64_t>(upc, units - u0);
+    const int64_t nu = sched[idx];
     // staging buffer b is free once the D2H (or compute) of chunk idx-2 finished
     if (idx >= 2) {
       TIC_CUDA(h, cudaStreamWaitEvent(h->s_h2d, inout_same ? h->ev_out[b] : h->ev_comp[b], 0));
@@ -1059,7 +1088,9 @@ int tic_roundtrip_images(tic_codec* h, const uint8_t* images, int64_t n_images, 
   TIC_CUDA(h, cudaSetDevice(h->device));
   const Geo g0 = image_geo(H, W, P, 0);
   const int ppi = g0.gh * g0.gw;
-  const int64_t ipc = host_units_per_chunk(n_images, std::max<int64_t>(1, patches_per_chunk(h, P) / ppi), (double)ppi * P * P / 16384.0);
+  const std::vector<int64_t> sched =
+      host_chunk_schedule(n_images, std::max<int64_t>(1, patches_per_chunk(h, P) / ppi), (double)ppi * P * P / 16384.0);
+  const int64_t ipc = *std::max_element(sched.begin(), sched.end());
   const size_t img_unit = (size_t)H * W * 3;
   const size_t sym_unit = (size_t)ppi * hb * wb * cb;
   const size_t rec_unit = img_unit * (out_dtype == TIC_U8 ? 1 : 4);
@@ -1081,10 +1112,10 @@ int tic_roundtrip_images(tic_codec* h, const uint8_t* images, int64_t n_images, 
   // Three streams, two staging sets: H2D of chunk i+1 (one PCIe direction) runs under the kernels of chunk i and
   // the D2H of chunk i-1 (the other direction).
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
-  int64_t idx = 0;
-  for (int64_t u0 = 0; u0 < n_images; u0 += ipc, ++idx) {
+  int64_t u0 = 0;
+  for (int64_t idx = 0; idx < (int64_t)sched.size(); u0 += sched[idx], ++idx) {
     const int b = (int)(idx & 1);
-    const int64_t nu = std::min<int64_t>(ipc, n_images - u0);
+    const int64_t nu = sched[idx];
     if (idx >= 2) TIC_CUDA(h, cudaStreamWaitEvent(h->s_h2d, h->ev_enc[b], 0));  // encoder of chunk idx-2 consumed stage_in[b]
     TIC_CUDA(h, cudaMemcpyAsync(h->stage_in[b], images + (size_t)u0 * img_unit, (size_t)nu * img_unit, cudaMemcpyHostToDevice,
                                 h->s_h2d));

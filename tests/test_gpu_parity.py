@@ -335,6 +335,18 @@ def test_cfg4_distribution_table_and_bitstreams(mode, tmp_path):
             assert ref_path.read_bytes() == open(path, "rb").read()
         assert nbytes == os.path.getsize(path)
         k += npatch
+    # bpp delta (BASELINE metric): the oracle's symbols through the same coder and table
+    ref_bytes, k = [], 0
+    for im in images:
+        npatch = len(O.crop_image_input_patches(im, 128))
+        e = range_coder.RangeEncoder(str(tmp_path / "ref_bpp.bin"))
+        e.encode(ref_sym[k:k + npatch].reshape(-1), cum)
+        e.close()
+        ref_bytes.append(os.path.getsize(tmp_path / "ref_bpp.bin"))
+        k += npatch
+    bpp_gpu, bpp_ref = entry.bpp([b for _, b in out], images), entry.bpp(ref_bytes, images)
+    assert abs(bpp_gpu - bpp_ref) <= 1e-4 * bpp_ref, (bpp_gpu, bpp_ref)
+    oracle_sym = ref_sym
     ref_sym = gpu_sym  # the decode side is checked on the symbols that were actually coded
     rec = entry.uncompress(codec, str(tmp_path / "enc"), cfg, prob)
     assert sorted(rec) == [f"img_{i}" for i in range(len(images))]
@@ -345,7 +357,17 @@ def test_cfg4_distribution_table_and_bitstreams(mode, tmp_path):
         d = np.abs(rec[f"img_{i}"].astype(int) - want.astype(int))
         assert rec[f"img_{i}"].shape == im.shape and d.max() <= 1 and (d != 0).mean() < 1e-4
         k += npatch
-    assert entry.bpp([b for _, b in out], images) > 0 and np.isfinite(entry.psnr(images, [rec[f"img_{i}"] for i in range(len(images))]))
+    # PSNR delta (BASELINE metric, north_star: within 0.01 dB): the oracle's own round trip (its symbols, its decoder)
+    wants, k = [], 0
+    for im in images:
+        npatch = len(O.crop_image_input_patches(im, 128))
+        wants.append(O.around_u8(O.concat_patches(list(O.decoder(oracle_sym[k:k + npatch], variant, dec, MEAN, STD, 2)),
+                                                  im.shape[0], im.shape[1], 128)))
+        k += npatch
+    psnr_gpu = entry.psnr(images, [rec[f"img_{i}"] for i in range(len(images))])
+    psnr_ref = entry.psnr(images, wants)
+    assert np.isfinite(psnr_gpu) and abs(psnr_gpu - psnr_ref) <= 0.01, (psnr_gpu, psnr_ref)
+    assert bpp_gpu > 0
     codec.close()
 
 
@@ -431,3 +453,15 @@ def test_restore_params_from_tf_v2_checkpoint(tmp_path):
     with pytest.raises(FileNotFoundError):
         K.restore_params(fresh, params_file=str(tmp_path / "absent" / "params"))
     fresh.close()
+
+
+def test_nccl_table_allreduce():
+    """The path's one collective on real GPUs (needs two): tests/nccl_table_check.py under torchrun."""
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2); the gloo world-size-2 test covers the host logic on CPU")
+    script = os.path.join(os.path.dirname(__file__), "nccl_table_check.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "nccl table check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -445,6 +445,13 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
         a.bias = ly.b;
         a.q = h->q;
         a.hist = h->d_hist;
+        {
+          static const int dbg = [] {
+            const char* e = getenv("TIC_DBG");
+            return e ? atoi(e) : 0;
+          }();
+          a.dbg = dbg;
+        }
         for (int c = 0; c < 3; ++c) {
           a.mean[c] = g.mean[c];
           a.stdv[c] = g.stdv[c];

@@ -123,6 +123,7 @@ struct LayerArgs {
   // IO_ACT16 tensors: `in` / `out` / `res` point at the hi plane, the lo' plane starts *_lo_off halves later
   long long in_lo_off, out_lo_off, res_lo_off;
   int res16;             // residual source is a pair-plane tensor
+  int dbg;               // measurement aid (env TIC_DBG bit 8: the staged epilogue skips its global stores)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act ? fmaxf(v, 0.0f) : v; }

@@ -668,7 +668,7 @@ __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, c
         const int base = __shfl_sync(0xffffffffu, my_off16, owner);
         const int sw = (sp_ix >> FSH) & (M - 1);
         const uint4 val = lds128(stage + (uint32_t)((sp_ix * M + (cq ^ sw)) << 4));
-        if (base >= 0) plane[(long long)base + row_off16 + (kPh ? (sp_ix & 1) * row16 : 0) + cq] = val;
+        if (base >= 0 && !(a.dbg & 8)) plane[(long long)base + row_off16 + (kPh ? (sp_ix & 1) * row16 : 0) + cq] = val;
       }
       __syncwarp();
     };

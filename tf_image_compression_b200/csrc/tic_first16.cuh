@@ -669,6 +669,275 @@ f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params 
   }
 }
 
+// ---- stride 2, TMA-fed, pair-plane output: the hot configuration of every codec variant ---------------------
+// Same operands and MMAs as f16_first_s2_kernel, but sized for thread-level parallelism in the epilogue: its fixed
+// per-tile chain (accumulator wait, TMEM load, stage, two flushes) cost 570 cycles per 128-pixel tile at two warps per
+// scheduler (epilogue alone, no stores: 1.70 ms against 0.93 ms for the same number of elements in decode_1's 4x
+// larger tiles).  Warps: 0-5 builders (165 live threads), 6 MMA + TMEM, 7 raw-window TMA, 8-23 epilogue = four groups
+// of four warps, group g owns TMEM buffer g = tiles it % 4 == g.  An epilogue warp stages BOTH planes of its 32
+// pixels (8 KB, no lo' words held in registers: <= 80 registers per thread at 768 threads) and flushes them in one pass.
+constexpr int kT2Builders = 6, kT2MmaWarp = 6, kT2TmaWarp = 7, kT2EpiWarp0 = 8, kT2EpiWarps = 16;
+constexpr int kT2Threads = 32 * (kT2EpiWarp0 + kT2EpiWarps);
+constexpr uint32_t kT2StagePerWarp = 8192;
+
+template <int CEND>
+__device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const uint32_t tbuf, const int NPAD, const int n, const int yt,
+                                                     const int xt, const float* s_bias, const uint32_t stage, const int lane,
+                                                     uint64_t* rel_bar) {
+  constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane
+  constexpr int MSH = M == 2 ? 1 : 2;
+  constexpr int FSH = 3 - MSH;                       // swizzle: chunk ^= (pixel >> FSH) & (M - 1)
+  constexpr int NCI = CEND / 16;
+  const float floor_v = a.act ? 0.0f : -INFINITY;
+  const long long pix0 = ((long long)n * a.hout + yt) * a.wout + xt;
+  const int my_off16 = (int)((pix0 * a.cout * 2) >> 4);   // this lane's pixel row inside a plane, 16-byte units
+  const uint32_t sp = stage + (uint32_t)lane * (M * 16);
+  const int sw = (lane >> FSH) & (M - 1);
+#pragma unroll
+  for (int ci = 0; ci < NCI; ++ci) {
+    float v[16], u[16];
+    ptx::tmem_ld16_nowait(tbuf + NPAD + ci * 16, u);
+    ptx::tmem_ld16_nowait(tbuf + ci * 16, v);
+    ptx::tmem_ld_wait();
+    if (ci == NCI - 1) {  // last TMEM read of the tile: hand the buffer back
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(rel_bar);
+    }
+    const float4* bp = reinterpret_cast<const float4*>(s_bias + ci * 16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 b = bp[i];
+      v[4 * i] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i], 1.0f / 2048.0f, v[4 * i]), b.x), floor_v);
+      v[4 * i + 1] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 1], 1.0f / 2048.0f, v[4 * i + 1]), b.y), floor_v);
+      v[4 * i + 2] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 2], 1.0f / 2048.0f, v[4 * i + 2]), b.z), floor_v);
+      v[4 * i + 3] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 3], 1.0f / 2048.0f, v[4 * i + 3]), b.w), floor_v);
+    }
+    uint32_t hp[8], lp[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
+    sts128(sp + (uint32_t)(((2 * ci) ^ sw) << 4), hp[0], hp[1], hp[2], hp[3]);
+    sts128(sp + (uint32_t)(((2 * ci + 1) ^ sw) << 4), hp[4], hp[5], hp[6], hp[7]);
+    sts128(sp + 4096u + (uint32_t)(((2 * ci) ^ sw) << 4), lp[0], lp[1], lp[2], lp[3]);
+    sts128(sp + 4096u + (uint32_t)(((2 * ci + 1) ^ sw) << 4), lp[4], lp[5], lp[6], lp[7]);
+  }
+  __syncwarp();
+  // write back: chunk q of the stage -> its pixel's row; a warp's 8-pixel rows are contiguous 512-byte (M = 4) runs
+  uint4* const ohi = reinterpret_cast<uint4*>(a.out);
+  uint4* const olo = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.out) + a.out_lo_off);
+#pragma unroll
+  for (int j = 0; j < M; ++j) {
+    const int q = lane + 32 * j;
+    const int px = q >> MSH, cq = q & (M - 1);
+    const int base = __shfl_sync(0xffffffffu, my_off16, px);
+    const int swq = (px >> FSH) & (M - 1);
+    const uint32_t src = stage + (uint32_t)((px * M + (cq ^ swq)) << 4);
+    const uint4 vh = lds128(src), vl = lds128(src + 4096u);
+    if (!(a.dbg & 8)) {
+      ohi[(long long)base + cq] = vh;
+      olo[(long long)base + cq] = vl;
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(kT2Threads, 1)
+f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params p, const LayerArgs a) {
+  const int NPAD = p.npad;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_a = smem;                                  // kW2Stages stages
+  uint8_t* s_w = smem + kW2Stages * 10240;              // 192 * npad bytes
+  uint8_t* s_stage = s_w + 192 * 64;                    // 16 x 8 KB epilogue stages (hi | lo')
+  uint8_t* s_rawwin = s_stage + kT2EpiWarps * kT2StagePerWarp;
+  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_rawwin + kRawStages * kRawStage);
+  __shared__ __align__(16) float s_bias[128];
+  __shared__ uint32_t s_plut[3 * 256];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid < 128) s_bias[tid] = (tid < NPAD && tid < a.cout) ? a.bias[tid] : 0.f;
+  for (int i = tid; i < 3 * 256; i += kT2Threads) {
+    __half hi, lo;
+    split16(a.lut[i], hi, lo);
+    s_plut[i] = pack_half2(hi, lo);
+  }
+  for (int i = tid; i < 12 * NPAD; i += kT2Threads)
+    reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
+  if (tid == 0) {
+    for (int i = 0; i < kW2Stages; ++i) {
+      ptx::mbar_init(&bars->full[i], kT2Builders);
+      ptx::mbar_init(&bars->empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      ptx::mbar_init(&bars->acc_full[i], 1);
+      ptx::mbar_init(&bars->acc_empty[i], 4);
+    }
+    for (int i = 0; i < kRawStages; ++i) {
+      ptx::mbar_init(&bars->raw_full[i], 1);
+      ptx::mbar_init(&bars->raw_empty[i], kT2Builders);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == kT2MmaWarp) {
+    ptx::tmem_alloc(&bars->tmem_base, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const uint32_t pairw = 2u * (uint32_t)NPAD;
+
+  if (warp < kT2Builders) {
+    // ===== builders: thread = (row, quad of 4 pixels); 33 x 5 = 165 threads; quad 4 holds pixels 16, 17 =====
+    const int ry = tid / 5, qx = tid - ry * 5;
+    const bool live = ry < kW2Rows;
+    const uint32_t my_raw = (uint32_t)ry * kRawRow + (uint32_t)qx * 12u;
+    const uint32_t my_dst = (uint32_t)(ry * kW2Cols + 4 * qx) * 8u;
+    const int npx = qx == 4 ? 2 : 4;
+    uint32_t r = 0, rph = 0, s = 0, sph = 1;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      unsigned n, rt, ty, tx;
+      fast_divmod((unsigned)tile, p.txy_d, n, rt);
+      fast_divmod(rt, p.tx_d, ty, tx);
+      const int iy = 32 * (int)ty + ry, ix = 16 * (int)tx + 4 * qx;
+      ptx::mbar_wait(&bars->raw_full[r], rph);
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+      if (live) {
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(s_rawwin + (size_t)r * kRawStage + my_raw);
+        w0 = rp[0];
+        w1 = rp[1];
+        w2 = rp[2];
+      }
+      uint2 vh[4], vl[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
+        const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
+        const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
+        const bool okj = live && iy < p.P && ix + j < p.P;
+        const uint32_t x0 = okj ? s_plut[b0] : 0u;
+        const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
+        const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
+        vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
+        vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->raw_empty[r]);
+      if (++r == kRawStages) {
+        r = 0;
+        rph ^= 1u;
+      }
+      ptx::mbar_wait(&bars->empty[s], sph);
+      if (live) {
+        uint8_t* st = s_a + (size_t)s * 10240 + my_dst;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < npx) {
+            *reinterpret_cast<uint2*>(st + j * 8) = vh[j];
+            *reinterpret_cast<uint2*>(st + kW2Plane + j * 8) = vl[j];
+          }
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
+      if (++s == kW2Stages) {
+        s = 0;
+        sph ^= 1u;
+      }
+    }
+  } else if (warp == kT2TmaWarp) {
+    // ===== raw-window producer =====
+    const Geo g = a.geo;
+    if (ptx::elect_one()) ptx::prefetch_tmap(&tm_img);
+    __syncwarp();
+    uint32_t r = 0, rph = 1;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&bars->raw_empty[r], rph);
+      if (ptx::elect_one()) {
+        unsigned n, rt, ty, tx, img, gy, gx;
+        fast_divmod((unsigned)tile, p.txy_d, n, rt);
+        fast_divmod(rt, p.tx_d, ty, tx);
+        geo_decode(g, (unsigned)g.n0 + n, img, gy, gx);
+        const int Yb = (int)gy * g.P + 32 * (int)ty, Xb = (int)gx * g.P + 16 * (int)tx;
+        ptx::mbar_expect_tx(&bars->raw_full[r], kW2Rows * kRawRow);
+        ptx::tma_load_3d(s_rawwin + (size_t)r * kRawStage, &tm_img, &bars->raw_full[r], Xb * 3, Yb, (int)img);
+      }
+      __syncwarp();
+      if (++r == kRawStages) {
+        r = 0;
+        rph ^= 1u;
+      }
+    }
+  } else if (warp == kT2MmaWarp) {
+    // ===== MMA issuer: per tile 3 filter rows x (A_hi x [W_hi ; W_lo'] , A_lo' x W_hi); TMEM buffer = tile & 3 =====
+    const uint32_t idesc_st = ptx::make_idesc_f16(128, 2 * NPAD);
+    const uint32_t idesc_lo = ptx::make_idesc_f16(128, NPAD);
+    const uint32_t a_hi32 = ((2u * kW2Pitch) >> 4) | (1u << 14);
+    const uint32_t w_hi32 = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo = (16u >> 4) << 16, w_lbo = ((32u * (uint32_t)NPAD) >> 4) << 16;
+    const uint32_t wbase = (ptx::smem_u32(s_w) >> 4) | w_lbo;
+    uint32_t it = 0, s = 0, sph = 0;
+    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 3u;
+      ptx::mbar_wait(&bars->acc_empty[b], ((it >> 2) & 1) ^ 1);
+      ptx::mbar_wait(&bars->full[s], sph);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * 10240) >> 4) | a_lbo;
+        const uint32_t al = ah + (kW2Plane >> 4);
+        const uint32_t d = tmem_base + b * pairw;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t wd = wbase + (uint32_t)kh * ((64u * (uint32_t)NPAD) >> 4);
+          ptx::mma_f16_ss(d, u16_desc(ah + (uint32_t)kh * (kW2Pitch >> 4), a_hi32), u16_desc(wd, w_hi32), idesc_st, kh ? 1u : 0u);
+          ptx::mma_f16_ss(d + (uint32_t)NPAD, u16_desc(al + (uint32_t)kh * (kW2Pitch >> 4), a_hi32), u16_desc(wd, w_hi32), idesc_lo, 1u);
+        }
+      }
+      __syncwarp();
+      if (ptx::elect_one()) {
+        ptx::tc_commit(&bars->empty[s]);
+        ptx::tc_commit(&bars->acc_full[b]);
+      }
+      __syncwarp();
+      if (++s == kW2Stages) {
+        s = 0;
+        sph ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue: group g = TMEM buffer g = tiles it % 4 == g =====
+    const int ew = warp - kT2EpiWarp0;
+    const int q4 = warp & 3, group = ew >> 2;
+    const int m = q4 * 32 + lane;
+    const int hh = m >> 3, xx = m & 7;
+    const uint32_t stage = ptx::smem_u32(s_stage + (size_t)ew * kT2StagePerWarp);
+    const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)group * pairw;
+    uint32_t use = 0;
+    for (long long tile = blockIdx.x + (long long)group * gridDim.x; tile < p.num_tiles; tile += 4LL * gridDim.x, ++use) {
+      ptx::mbar_wait(&bars->acc_full[group], use & 1);
+      ptx::tc_fence_after();
+      uint32_t tq, tx, ty, tn;
+      fast_divmod((uint32_t)tile, p.tx_d, tq, tx);
+      fast_divmod(tq, p.ty_d, tn, ty);
+      if (NPAD == 32)
+        f16_t2_epilogue_tile<32>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group]);
+      else
+        f16_t2_epilogue_tile<16>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kT2MmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 inline bool f16_first_supported(const LayerArgs& a, int kind, int stride) {
   if (kind != 0 || a.cin != 3) return false;
   if (a.in_mode != IO_U8_NORM && a.in_mode != IO_F32_NORM) return false;
@@ -772,7 +1041,24 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
       return fail("cudaFuncSetAttribute(first-layer kernel) failed", -2);
     configured = true;
   }
-  if (windowed)
+  // the TMA-fed, pair-plane-output kernel (16 epilogue warps) when the launch qualifies; TIC_FIRST_T2=0 keeps the general one
+  static const bool t2_off = [] {
+    const char* e = getenv("TIC_FIRST_T2");
+    return e && e[0] == '0';
+  }();
+  const bool t2 = windowed && p.use_tma && !t2_off && p.dbg == 0 && a.out_mode == IO_ACT16 && (a.cout == 32 || a.cout == 16) &&
+                  p.nbuf == 4;
+  if (t2) {
+    const size_t smem_t2 =
+        kW2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kRawStages * kRawStage + sizeof(W2SmemBars) + 1024;
+    static bool t2_configured = false;
+    if (!t2_configured) {
+      if (cudaFuncSetAttribute(f16_first_s2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t2) != cudaSuccess)
+        return fail("cudaFuncSetAttribute(first-layer TMA kernel) failed", -2);
+      t2_configured = true;
+    }
+    f16_first_s2_tma_kernel<<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
+  } else if (windowed)
     f16_first_s2_kernel<<<grid, kW2Threads, smem_w2, stream>>>(tm_img, p, a);
   else if (stride == 1)
     f16_first_kernel<1><<<grid, kF16Threads, smem, stream>>>(p, a);

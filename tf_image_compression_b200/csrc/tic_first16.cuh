@@ -678,7 +678,14 @@ f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params 
 // pixels (8 KB, no lo' words held in registers: <= 80 registers per thread at 768 threads) and flushes them in one pass.
 constexpr int kT2Builders = 6, kT2MmaWarp = 6, kT2TmaWarp = 7, kT2EpiWarp0 = 8, kT2EpiWarps = 16;
 constexpr int kT2Threads = 32 * (kT2EpiWarp0 + kT2EpiWarps);
-constexpr uint32_t kT2StagePerWarp = 8192;
+constexpr uint32_t kT2StagePerWarp = 4096;        // hi plane | lo' plane of 32 pixels x 32 channels
+constexpr uint32_t kT2LoOff = 2048;
+// f32 images (rmbe post-filter, submit/2/rmbe/rmbe.py:15-111): the raw window is 33 rows x 18 pixels x 12 bytes, fetched
+// as a 33 x 224-byte box (56 floats); a builder thread owns 4 pixels = three aligned 16-byte words and normalises with
+// the reference's true division (model.py:44) before the fp16 split.
+constexpr uint32_t kRawRowF32 = 224;
+constexpr uint32_t kRawStageF32 = 7424;            // 33 * 224 = 7392, padded to a multiple of 128
+constexpr int kRawStagesF32 = 4;
 
 template <int CEND>
 __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const uint32_t tbuf, const int NPAD, const int n, const int yt,
@@ -718,8 +725,8 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const u
     for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
     sts128(sp + (uint32_t)(((2 * ci) ^ sw) << 4), hp[0], hp[1], hp[2], hp[3]);
     sts128(sp + (uint32_t)(((2 * ci + 1) ^ sw) << 4), hp[4], hp[5], hp[6], hp[7]);
-    sts128(sp + 4096u + (uint32_t)(((2 * ci) ^ sw) << 4), lp[0], lp[1], lp[2], lp[3]);
-    sts128(sp + 4096u + (uint32_t)(((2 * ci + 1) ^ sw) << 4), lp[4], lp[5], lp[6], lp[7]);
+    sts128(sp + kT2LoOff + (uint32_t)(((2 * ci) ^ sw) << 4), lp[0], lp[1], lp[2], lp[3]);
+    sts128(sp + kT2LoOff + (uint32_t)(((2 * ci + 1) ^ sw) << 4), lp[4], lp[5], lp[6], lp[7]);
   }
   __syncwarp();
   // write back: chunk q of the stage -> its pixel's row; a warp's 8-pixel rows are contiguous 512-byte (M = 4) runs
@@ -732,7 +739,7 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const u
     const int base = __shfl_sync(0xffffffffu, my_off16, px);
     const int swq = (px >> FSH) & (M - 1);
     const uint32_t src = stage + (uint32_t)((px * M + (cq ^ swq)) << 4);
-    const uint4 vh = lds128(src), vl = lds128(src + 4096u);
+    const uint4 vh = lds128(src), vl = lds128(src + kT2LoOff);
     if (!(a.dbg & 8)) {
       ohi[(long long)base + cq] = vh;
       olo[(long long)base + cq] = vl;
@@ -741,8 +748,21 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const u
   __syncwarp();
 }
 
+// (x - mean) / std for a launch-constant std without the division routine (~15 instructions, 12 per builder thread
+// and tile: it bounded the f32 first layer of rmbe at 3.4 ms per 5696 tiles): q0 = y * RN(1 / std), one residual
+// correction q = q0 + r * (y - std * q0) with the residual exact in an FMA (Markstein) — the correctly rounded quotient
+// for these operand ranges; any last-ulp disagreement with the division is 4x below the fp16-pair format's own 2^-22.
+__device__ __forceinline__ float f16_norm_fast(float x, float mean, float stdv, float rstd) {
+  const float y = __fsub_rn(x, mean);
+  const float q0 = __fmul_rn(y, rstd);
+  return __fmaf_rn(__fmaf_rn(-stdv, q0, y), rstd, q0);
+}
+
+template <bool F32>
 __global__ void __launch_bounds__(kT2Threads, 1)
 f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params p, const LayerArgs a) {
+  constexpr uint32_t RAW_ROW = F32 ? kRawRowF32 : kRawRow, RAW_STAGE = F32 ? kRawStageF32 : kRawStage;
+  constexpr uint32_t RAW_STAGES = F32 ? kRawStagesF32 : kRawStages;
   const int NPAD = p.npad;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -750,18 +770,19 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
   uint8_t* s_w = smem + kW2Stages * 10240;              // 192 * npad bytes
   uint8_t* s_stage = s_w + 192 * 64;                    // 16 x 8 KB epilogue stages (hi | lo')
   uint8_t* s_rawwin = s_stage + kT2EpiWarps * kT2StagePerWarp;
-  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_rawwin + kRawStages * kRawStage);
+  W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_rawwin + RAW_STAGES * RAW_STAGE);
   __shared__ __align__(16) float s_bias[128];
   __shared__ uint32_t s_plut[3 * 256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid < 128) s_bias[tid] = (tid < NPAD && tid < a.cout) ? a.bias[tid] : 0.f;
-  for (int i = tid; i < 3 * 256; i += kT2Threads) {
-    __half hi, lo;
-    split16(a.lut[i], hi, lo);
-    s_plut[i] = pack_half2(hi, lo);
-  }
+  if (!F32)
+    for (int i = tid; i < 3 * 256; i += kT2Threads) {
+      __half hi, lo;
+      split16(a.lut[i], hi, lo);
+      s_plut[i] = pack_half2(hi, lo);
+    }
   for (int i = tid; i < 12 * NPAD; i += kT2Threads)
     reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (tid == 0) {
@@ -773,7 +794,7 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
       ptx::mbar_init(&bars->acc_full[i], 1);
       ptx::mbar_init(&bars->acc_empty[i], 4);
     }
-    for (int i = 0; i < kRawStages; ++i) {
+    for (int i = 0; i < (int)RAW_STAGES; ++i) {
       ptx::mbar_init(&bars->raw_full[i], 1);
       ptx::mbar_init(&bars->raw_empty[i], kT2Builders);
     }
@@ -794,7 +815,8 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     // ===== builders: thread = (row, quad of 4 pixels); 33 x 5 = 165 threads; quad 4 holds pixels 16, 17 =====
     const int ry = tid / 5, qx = tid - ry * 5;
     const bool live = ry < kW2Rows;
-    const uint32_t my_raw = (uint32_t)ry * kRawRow + (uint32_t)qx * 12u;
+    const float rstd0 = __frcp_rn(a.stdv[0]), rstd1 = __frcp_rn(a.stdv[1]), rstd2 = __frcp_rn(a.stdv[2]);
+    const uint32_t my_raw = (uint32_t)ry * RAW_ROW + (uint32_t)qx * (F32 ? 48u : 12u);
     const uint32_t my_dst = (uint32_t)(ry * kW2Cols + 4 * qx) * 8u;
     const int npx = qx == 4 ? 2 : 4;
     uint32_t r = 0, rph = 0, s = 0, sph = 1;
@@ -804,29 +826,52 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
       fast_divmod(rt, p.tx_d, ty, tx);
       const int iy = 32 * (int)ty + ry, ix = 16 * (int)tx + 4 * qx;
       ptx::mbar_wait(&bars->raw_full[r], rph);
-      uint32_t w0 = 0, w1 = 0, w2 = 0;
-      if (live) {
-        const uint32_t* rp = reinterpret_cast<const uint32_t*>(s_rawwin + (size_t)r * kRawStage + my_raw);
-        w0 = rp[0];
-        w1 = rp[1];
-        w2 = rp[2];
-      }
       uint2 vh[4], vl[4];
+      if (F32) {
+        float f[12];
+        if (live) {
+          const float4* rp = reinterpret_cast<const float4*>(s_rawwin + (size_t)r * RAW_STAGE + my_raw);
+          const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+          f[0] = q0.x, f[1] = q0.y, f[2] = q0.z, f[3] = q0.w;
+          f[4] = q1.x, f[5] = q1.y, f[6] = q1.z, f[7] = q1.w;
+          f[8] = q2.x, f[9] = q2.y, f[10] = q2.z, f[11] = q2.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
-        const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
-        const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
-        const bool okj = live && iy < p.P && ix + j < p.P;
-        const uint32_t x0 = okj ? s_plut[b0] : 0u;
-        const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
-        const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
-        vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
-        vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
+          for (int i = 0; i < 12; ++i) f[i] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool okj = live && iy < p.P && ix + j < p.P;
+          const float f0 = okj ? f16_norm_fast(f[3 * j], a.mean[0], a.stdv[0], rstd0) : 0.f;
+          const float f1 = okj ? f16_norm_fast(f[3 * j + 1], a.mean[1], a.stdv[1], rstd1) : 0.f;
+          const float f2 = okj ? f16_norm_fast(f[3 * j + 2], a.mean[2], a.stdv[2], rstd2) : 0.f;
+          split16x2(f0, f1, vh[j].x, vl[j].x);
+          split16x2(f2, 0.f, vh[j].y, vl[j].y);
+        }
+      } else {
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (live) {
+          const uint32_t* rp = reinterpret_cast<const uint32_t*>(s_rawwin + (size_t)r * RAW_STAGE + my_raw);
+          w0 = rp[0];
+          w1 = rp[1];
+          w2 = rp[2];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
+          const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
+          const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
+          const bool okj = live && iy < p.P && ix + j < p.P;
+          const uint32_t x0 = okj ? s_plut[b0] : 0u;
+          const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
+          const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
+          vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
+          vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
+        }
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->raw_empty[r]);
-      if (++r == kRawStages) {
+      if (++r == RAW_STAGES) {
         r = 0;
         rph ^= 1u;
       }
@@ -862,12 +907,12 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
         fast_divmod((unsigned)tile, p.txy_d, n, rt);
         fast_divmod(rt, p.tx_d, ty, tx);
         geo_decode(g, (unsigned)g.n0 + n, img, gy, gx);
-        const int Yb = (int)gy * g.P + 32 * (int)ty, Xb = (int)gx * g.P + 16 * (int)tx;
-        ptx::mbar_expect_tx(&bars->raw_full[r], kW2Rows * kRawRow);
-        ptx::tma_load_3d(s_rawwin + (size_t)r * kRawStage, &tm_img, &bars->raw_full[r], Xb * 3, Yb, (int)img);
+        const int Yb = g.oy + (int)gy * g.P + 32 * (int)ty, Xb = g.ox + (int)gx * g.P + 16 * (int)tx;
+        ptx::mbar_expect_tx(&bars->raw_full[r], kW2Rows * RAW_ROW);
+        ptx::tma_load_3d(s_rawwin + (size_t)r * RAW_STAGE, &tm_img, &bars->raw_full[r], Xb * 3, Yb, (int)img);
       }
       __syncwarp();
-      if (++r == kRawStages) {
+      if (++r == RAW_STAGES) {
         r = 0;
         rph ^= 1u;
       }
@@ -953,9 +998,11 @@ inline bool f16_first_supported(const LayerArgs& a, int kind, int stride) {
 // offset), and a global address / row pitch the tensor map accepts (16-byte multiples).
 inline bool f16_first_tma_ok(const LayerArgs& a) {
   const Geo& g = a.geo;
-  if (a.in_mode != IO_U8_NORM) return false;
-  if (g.oy != 0 || g.ox != 0 || g.H != g.gh * g.P || g.W != g.gw * g.P || g.P != a.hin) return false;
-  if ((g.W * 3) % 16 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15u) != 0) return false;
+  if (a.in_mode != IO_U8_NORM && a.in_mode != IO_F32_NORM) return false;
+  // the patch grid lies inside the image: no reflect padding (rmbe tile grids are inside by construction)
+  if (g.oy < 0 || g.ox < 0 || g.oy + g.gh * g.P > g.H || g.ox + g.gw * g.P > g.W || g.P != a.hin) return false;
+  const size_t row_bytes = (size_t)g.W * 3 * (a.in_mode == IO_U8_NORM ? 1 : 4);
+  if (row_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(a.in) & 15u) != 0) return false;
   if (a.hin % 32 != 0) return false;
   return true;
 }
@@ -1022,11 +1069,14 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
       const Geo& g = a.geo;
       const long long per_img = (long long)g.gh * g.gw;
       const cuuint64_t nimg = (cuuint64_t)((g.n0 + a.n + per_img - 1) / per_img);
+      const bool f32in = a.in_mode == IO_F32_NORM;
+      const cuuint64_t eb = f32in ? 4 : 1;
       cuuint64_t dims[3] = {(cuuint64_t)g.W * 3, (cuuint64_t)g.H, nimg};
-      cuuint64_t strides[2] = {(cuuint64_t)g.W * 3, (cuuint64_t)g.H * g.W * 3};
-      cuuint32_t box[3] = {kRawRow, (cuuint32_t)kW2Rows, 1};
+      cuuint64_t strides[2] = {(cuuint64_t)g.W * 3 * eb, (cuuint64_t)g.H * g.W * 3 * eb};
+      cuuint32_t box[3] = {f32in ? kRawRowF32 / 4 : kRawRow, (cuuint32_t)kW2Rows, 1};
       cuuint32_t es[3] = {1, 1, 1};
-      CUresult r = encode(&tm_img, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(a.in), dims, strides, box, es,
+      CUresult r = encode(&tm_img, f32in ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                          const_cast<void*>(a.in), dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r == CUDA_SUCCESS) p.use_tma = 1;
@@ -1048,16 +1098,25 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   }();
   const bool t2 = windowed && p.use_tma && !t2_off && p.dbg == 0 && a.out_mode == IO_ACT16 && (a.cout == 32 || a.cout == 16) &&
                   p.nbuf == 4;
+  // the general kernel's TMA builders take u8 windows of an un-shifted grid only
+  if (!t2 && (a.in_mode != IO_U8_NORM || a.geo.oy != 0 || a.geo.ox != 0)) p.use_tma = 0;
   if (t2) {
-    const size_t smem_t2 =
-        kW2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kRawStages * kRawStage + sizeof(W2SmemBars) + 1024;
+    const bool f32in = a.in_mode == IO_F32_NORM;
+    const size_t smem_t2 = kW2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp +
+                           (f32in ? kRawStagesF32 * kRawStageF32 : kRawStages * kRawStage) + sizeof(W2SmemBars) + 1024;
     static bool t2_configured = false;
     if (!t2_configured) {
-      if (cudaFuncSetAttribute(f16_first_s2_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t2) != cudaSuccess)
+      const int big = (int)(kW2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kRawStagesF32 * kRawStageF32 +
+                            sizeof(W2SmemBars) + 1024);
+      if (cudaFuncSetAttribute(f16_first_s2_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
+          cudaFuncSetAttribute(f16_first_s2_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess)
         return fail("cudaFuncSetAttribute(first-layer TMA kernel) failed", -2);
       t2_configured = true;
     }
-    f16_first_s2_tma_kernel<<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
+    if (f32in)
+      f16_first_s2_tma_kernel<true><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
+    else
+      f16_first_s2_tma_kernel<false><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
   } else if (windowed)
     f16_first_s2_kernel<<<grid, kW2Threads, smem_w2, stream>>>(tm_img, p, a);
   else if (stride == 1)

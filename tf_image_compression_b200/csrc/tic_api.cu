@@ -562,7 +562,8 @@ int patches_per_chunk(const tic_codec* h, int P) {
 // patches of 128x128 (measured on the 64-image round trip: 8 / 12 / 16 / 24 chunks -> 12.8 / 12.9 / 13.2 / 13.1
 // Gpixel/s).  A ramped schedule (chunks doubling from 384 patches to the workspace chunk and halving again:
 // 2, 4, 8, 18, 18, 8, 4, 2 images) was measured SLOWER (11.3 Gpixel/s): the round trip is bound by the D2H direction
-// running next to the H2D (654 MB at ~45 GB/s under duplex load), and large chunks leave it idle at both ends.
+// running next to the H2D (654 MB at 50 GB/s under duplex load, tools/pcie_probe.py), and large chunks leave it idle
+// at both ends.
 // TIC_HOST_RAMP=1 selects the ramp, TIC_HOST_CHUNKS the equal-chunk count.
 std::vector<int64_t> host_chunk_schedule(int64_t units, int64_t cap, double patches128_per_unit) {
   static const bool ramp = getenv("TIC_HOST_RAMP") != nullptr;

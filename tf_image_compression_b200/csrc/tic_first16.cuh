@@ -820,6 +820,24 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     const uint32_t my_dst = (uint32_t)(ry * kW2Cols + 4 * qx) * 8u;
     const int npx = qx == 4 ? 2 : 4;
     uint32_t r = 0, rph = 0, s = 0, sph = 1;
+    if (p.dbg & 2) {  // measurement aid: consume the raw windows, publish empty stages
+      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&bars->raw_full[r], rph);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->raw_empty[r]);
+        if (++r == RAW_STAGES) {
+          r = 0;
+          rph ^= 1u;
+        }
+        ptx::mbar_wait(&bars->empty[s], sph);
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
+        if (++s == kW2Stages) {
+          s = 0;
+          sph ^= 1u;
+        }
+      }
+    } else
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       unsigned n, rt, ty, tx;
       fast_divmod((unsigned)tile, p.txy_d, n, rt);
@@ -931,7 +949,7 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
       ptx::mbar_wait(&bars->acc_empty[b], ((it >> 2) & 1) ^ 1);
       ptx::mbar_wait(&bars->full[s], sph);
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
+      if (!(p.dbg & 1) && ptx::elect_one()) {
         const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * 10240) >> 4) | a_lbo;
         const uint32_t al = ah + (kW2Plane >> 4);
         const uint32_t d = tmem_base + b * pairw;
@@ -968,7 +986,11 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
       uint32_t tq, tx, ty, tn;
       fast_divmod((uint32_t)tile, p.tx_d, tq, tx);
       fast_divmod(tq, p.ty_d, tn, ty);
-      if (NPAD == 32)
+      if (p.dbg & 4) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[group]);
+      } else if (NPAD == 32)
         f16_t2_epilogue_tile<32>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group]);
       else
         f16_t2_epilogue_tile<16>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group]);
@@ -1096,7 +1118,7 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
     const char* e = getenv("TIC_FIRST_T2");
     return e && e[0] == '0';
   }();
-  const bool t2 = windowed && p.use_tma && !t2_off && p.dbg == 0 && a.out_mode == IO_ACT16 && (a.cout == 32 || a.cout == 16) &&
+  const bool t2 = windowed && p.use_tma && !t2_off && a.out_mode == IO_ACT16 && (a.cout == 32 || a.cout == 16) &&
                   p.nbuf == 4;
   // the general kernel's TMA builders take u8 windows of an un-shifted grid only
   if (!t2 && (a.in_mode != IO_U8_NORM || a.geo.oy != 0 || a.geo.ox != 0)) p.use_tma = 0;

@@ -465,3 +465,23 @@ def test_nccl_table_allreduce():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                         "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "nccl table check ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_full_size_roundtrip_host_equals_device():
+    """BASELINE config 2 at a quarter of one GPU's share (16 x 2048x1536, 3072 patches): the streamed host-to-host round
+    trip (16 chunks, both PCIe directions busy) is bit-identical to the device-resident calls, twice in a row."""
+    codec, enc, dec = make_codec("model_0", "fanin", compute="tensor")
+    rs = np.random.RandomState(4321)
+    imgs = torch.from_numpy(rs.randint(0, 256, size=(16, 1536, 2048, 3), dtype=np.uint8)).pin_memory()
+    d_imgs = imgs.cuda()
+    sym = codec.encode_images(d_imgs, 128)
+    rec = codec.decode_images(sym, 1536, 2048, 128)
+    out = torch.empty((16, 1536, 2048, 3), dtype=torch.uint8).pin_memory()
+    osym = torch.empty(tuple(sym.shape), dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        out.zero_()
+        codec.roundtrip_images(imgs, 128, out=out, out_symbols=osym)
+        assert torch.equal(osym, sym.cpu()) and torch.equal(out, rec.cpu())
+    # error of the codec itself is irrelevant here (random-free fan-in weights); the crop -> stitch geometry is not:
+    assert tuple(out.shape) == tuple(imgs.shape)
+    codec.close()

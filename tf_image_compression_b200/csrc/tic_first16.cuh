@@ -316,7 +316,7 @@ __global__ void f16_build_weights_s2_kernel(const float* __restrict__ w, int cou
 }
 
 struct W2SmemBars {
-  uint64_t full[kW2Stages], empty[kW2Stages];
+  uint64_t full[8], empty[8];        // kW2Stages (general kernel) | kT2Stages (TMA-fed kernel) in use
   uint64_t acc_full[4], acc_empty[4];
   uint64_t raw_full[kRawStages], raw_empty[kRawStages];
   uint32_t tmem_base;
@@ -686,6 +686,7 @@ constexpr uint32_t kT2LoOff = 2048;
 constexpr uint32_t kRawRowF32 = 224;
 constexpr uint32_t kRawStageF32 = 7424;            // 33 * 224 = 7392, padded to a multiple of 128
 constexpr int kRawStagesF32 = 4;
+constexpr int kT2Stages = 6;                       // operand stages = raw-window stages = builder warps (warp w owns slot w)
 
 template <int CEND>
 __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const uint32_t tbuf, const int NPAD, const int n, const int yt,
@@ -762,12 +763,12 @@ template <bool F32>
 __global__ void __launch_bounds__(kT2Threads, 1)
 f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params p, const LayerArgs a) {
   constexpr uint32_t RAW_ROW = F32 ? kRawRowF32 : kRawRow, RAW_STAGE = F32 ? kRawStageF32 : kRawStage;
-  constexpr uint32_t RAW_STAGES = F32 ? kRawStagesF32 : kRawStages;
+  constexpr uint32_t RAW_STAGES = kT2Stages;
   const int NPAD = p.npad;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* s_a = smem;                                  // kW2Stages stages
-  uint8_t* s_w = smem + kW2Stages * 10240;              // 192 * npad bytes
+  uint8_t* s_w = smem + kT2Stages * 10240;              // 192 * npad bytes
   uint8_t* s_stage = s_w + 192 * 64;                    // 16 x 8 KB epilogue stages (hi | lo')
   uint8_t* s_rawwin = s_stage + kT2EpiWarps * kT2StagePerWarp;
   W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_rawwin + RAW_STAGES * RAW_STAGE);
@@ -786,8 +787,8 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
   for (int i = tid; i < 12 * NPAD; i += kT2Threads)
     reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(p.wimg) + i);
   if (tid == 0) {
-    for (int i = 0; i < kW2Stages; ++i) {
-      ptx::mbar_init(&bars->full[i], kT2Builders);
+    for (int i = 0; i < kT2Stages; ++i) {
+      ptx::mbar_init(&bars->full[i], 1);
       ptx::mbar_init(&bars->empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) {
@@ -796,7 +797,7 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     }
     for (int i = 0; i < (int)RAW_STAGES; ++i) {
       ptx::mbar_init(&bars->raw_full[i], 1);
-      ptx::mbar_init(&bars->raw_empty[i], kT2Builders);
+      ptx::mbar_init(&bars->raw_empty[i], 1);
     }
     ptx::fence_barrier_init();
   }
@@ -812,104 +813,84 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
   const uint32_t pairw = 2u * (uint32_t)NPAD;
 
   if (warp < kT2Builders) {
-    // ===== builders: thread = (row, quad of 4 pixels); 33 x 5 = 165 threads; quad 4 holds pixels 16, 17 =====
-    const int ry = tid / 5, qx = tid - ry * 5;
-    const bool live = ry < kW2Rows;
+    // ===== builders: warp w builds the tiles it == w (mod 6) ALONE, into slot w: six tiles are in flight, and the 165
+    // (row, quad of 4 pixels) items of a tile are six independent passes per lane, so the shared-memory latencies of
+    // one pass hide under the next (six warps in lock-step on one tile ran at 12 cycles per instruction) =====
     const float rstd0 = __frcp_rn(a.stdv[0]), rstd1 = __frcp_rn(a.stdv[1]), rstd2 = __frcp_rn(a.stdv[2]);
-    const uint32_t my_raw = (uint32_t)ry * RAW_ROW + (uint32_t)qx * (F32 ? 48u : 12u);
-    const uint32_t my_dst = (uint32_t)(ry * kW2Cols + 4 * qx) * 8u;
-    const int npx = qx == 4 ? 2 : 4;
-    uint32_t r = 0, rph = 0, s = 0, sph = 1;
+    const uint32_t slot = (uint32_t)warp;
+    const uint8_t* rawb = s_rawwin + (size_t)slot * RAW_STAGE;
+    uint8_t* stb = s_a + (size_t)slot * 10240;
+    uint32_t ph = 0;
     if (p.dbg & 2) {  // measurement aid: consume the raw windows, publish empty stages
-      for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&bars->raw_full[r], rph);
+      for (long long tile = blockIdx.x + (long long)warp * gridDim.x; tile < p.num_tiles; tile += 6LL * gridDim.x, ph ^= 1u) {
+        ptx::mbar_wait(&bars->raw_full[slot], ph);
+        ptx::mbar_wait(&bars->empty[slot], ph ^ 1u);
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->raw_empty[r]);
-        if (++r == RAW_STAGES) {
-          r = 0;
-          rph ^= 1u;
-        }
-        ptx::mbar_wait(&bars->empty[s], sph);
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
-        if (++s == kW2Stages) {
-          s = 0;
-          sph ^= 1u;
+        if (lane == 0) {
+          ptx::mbar_arrive(&bars->raw_empty[slot]);
+          ptx::mbar_arrive(&bars->full[slot]);
         }
       }
     } else
-    for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    for (long long tile = blockIdx.x + (long long)warp * gridDim.x; tile < p.num_tiles; tile += 6LL * gridDim.x, ph ^= 1u) {
       unsigned n, rt, ty, tx;
       fast_divmod((unsigned)tile, p.txy_d, n, rt);
       fast_divmod(rt, p.tx_d, ty, tx);
-      const int iy = 32 * (int)ty + ry, ix = 16 * (int)tx + 4 * qx;
-      ptx::mbar_wait(&bars->raw_full[r], rph);
-      uint2 vh[4], vl[4];
-      if (F32) {
-        float f[12];
-        if (live) {
-          const float4* rp = reinterpret_cast<const float4*>(s_rawwin + (size_t)r * RAW_STAGE + my_raw);
-          const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-          f[0] = q0.x, f[1] = q0.y, f[2] = q0.z, f[3] = q0.w;
-          f[4] = q1.x, f[5] = q1.y, f[6] = q1.z, f[7] = q1.w;
-          f[8] = q2.x, f[9] = q2.y, f[10] = q2.z, f[11] = q2.w;
-        } else {
+      ptx::mbar_wait(&bars->raw_full[slot], ph);
+      ptx::mbar_wait(&bars->empty[slot], ph ^ 1u);
 #pragma unroll
-          for (int i = 0; i < 12; ++i) f[i] = 0.f;
-        }
+      for (int pass = 0; pass < 6; ++pass) {
+        const int item = pass * 32 + lane;
+        if (item < kW2Rows * 5) {
+          const int ry = item / 5, qx = item - ry * 5;
+          const int iy = 32 * (int)ty + ry, ix = 16 * (int)tx + 4 * qx;
+          const uint8_t* rp8 = rawb + (uint32_t)ry * RAW_ROW + (uint32_t)qx * (F32 ? 48u : 12u);
+          uint2 vh[4], vl[4];
+          if (F32) {
+            const float4* rp = reinterpret_cast<const float4*>(rp8);
+            const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+            const float f[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool okj = live && iy < p.P && ix + j < p.P;
-          const float f0 = okj ? f16_norm_fast(f[3 * j], a.mean[0], a.stdv[0], rstd0) : 0.f;
-          const float f1 = okj ? f16_norm_fast(f[3 * j + 1], a.mean[1], a.stdv[1], rstd1) : 0.f;
-          const float f2 = okj ? f16_norm_fast(f[3 * j + 2], a.mean[2], a.stdv[2], rstd2) : 0.f;
-          split16x2(f0, f1, vh[j].x, vl[j].x);
-          split16x2(f2, 0.f, vh[j].y, vl[j].y);
-        }
-      } else {
-        uint32_t w0 = 0, w1 = 0, w2 = 0;
-        if (live) {
-          const uint32_t* rp = reinterpret_cast<const uint32_t*>(s_rawwin + (size_t)r * RAW_STAGE + my_raw);
-          w0 = rp[0];
-          w1 = rp[1];
-          w2 = rp[2];
-        }
+            for (int j = 0; j < 4; ++j) {
+              const bool okj = iy < p.P && ix + j < p.P;
+              const float f0 = okj ? f16_norm_fast(f[3 * j], a.mean[0], a.stdv[0], rstd0) : 0.f;
+              const float f1 = okj ? f16_norm_fast(f[3 * j + 1], a.mean[1], a.stdv[1], rstd1) : 0.f;
+              const float f2 = okj ? f16_norm_fast(f[3 * j + 2], a.mean[2], a.stdv[2], rstd2) : 0.f;
+              split16x2(f0, f1, vh[j].x, vl[j].x);
+              split16x2(f2, 0.f, vh[j].y, vl[j].y);
+            }
+          } else {
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(rp8);
+            const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
-          const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
-          const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
-          const bool okj = live && iy < p.P && ix + j < p.P;
-          const uint32_t x0 = okj ? s_plut[b0] : 0u;
-          const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
-          const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
-          vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
-          vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars->raw_empty[r]);
-      if (++r == RAW_STAGES) {
-        r = 0;
-        rph ^= 1u;
-      }
-      ptx::mbar_wait(&bars->empty[s], sph);
-      if (live) {
-        uint8_t* st = s_a + (size_t)s * 10240 + my_dst;
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
+              const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
+              const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
+              const bool okj = iy < p.P && ix + j < p.P;
+              const uint32_t x0 = okj ? s_plut[b0] : 0u;
+              const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
+              const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
+              vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
+              vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
+            }
+          }
+          uint8_t* st = stb + (uint32_t)(ry * kW2Cols + 4 * qx) * 8u;
+          const int npx = qx == 4 ? 2 : 4;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < npx) {
-            *reinterpret_cast<uint2*>(st + j * 8) = vh[j];
-            *reinterpret_cast<uint2*>(st + kW2Plane + j * 8) = vl[j];
+          for (int j = 0; j < 4; ++j) {
+            if (j < npx) {
+              *reinterpret_cast<uint2*>(st + j * 8) = vh[j];
+              *reinterpret_cast<uint2*>(st + kW2Plane + j * 8) = vl[j];
+            }
           }
         }
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars->full[s]);
-      if (++s == kW2Stages) {
-        s = 0;
-        sph ^= 1u;
+      if (lane == 0) {
+        ptx::mbar_arrive(&bars->raw_empty[slot]);
+        ptx::mbar_arrive(&bars->full[slot]);
       }
     }
   } else if (warp == kT2TmaWarp) {
@@ -966,7 +947,7 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
         ptx::tc_commit(&bars->acc_full[b]);
       }
       __syncwarp();
-      if (++s == kW2Stages) {
+      if (++s == kT2Stages) {
         s = 0;
         sph ^= 1u;
       }
@@ -1124,11 +1105,11 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   if (!t2 && (a.in_mode != IO_U8_NORM || a.geo.oy != 0 || a.geo.ox != 0)) p.use_tma = 0;
   if (t2) {
     const bool f32in = a.in_mode == IO_F32_NORM;
-    const size_t smem_t2 = kW2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp +
-                           (f32in ? kRawStagesF32 * kRawStageF32 : kRawStages * kRawStage) + sizeof(W2SmemBars) + 1024;
+    const size_t smem_t2 = kT2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp +
+                           kT2Stages * (f32in ? kRawStageF32 : kRawStage) + sizeof(W2SmemBars) + 1024;
     static bool t2_configured = false;
     if (!t2_configured) {
-      const int big = (int)(kW2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kRawStagesF32 * kRawStageF32 +
+      const int big = (int)(kT2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kT2Stages * kRawStageF32 +
                             sizeof(W2SmemBars) + 1024);
       if (cudaFuncSetAttribute(f16_first_s2_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
           cudaFuncSetAttribute(f16_first_s2_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess)

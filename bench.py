@@ -90,6 +90,41 @@ def cpu_roundtrip_time(n_images, reps):
     return best, torch.get_num_threads()
 
 
+def parity_sample(compute):
+    """BASELINE metric's parity part on a bounded sample, next to the CPU baseline (rank 0, N = 1): one 256x384 synthetic
+    image, fan-in weights, GPU path vs the oracle — symbol mismatches, reconstruction difference, bpp and PSNR deltas
+    (processing_utils/evaluate.py:10-49) with the same table and range coder on both symbol streams."""
+    import tempfile
+    import tf_image_compression_b200 as T
+    from tf_image_compression_b200 import entry, range_coder
+    from oracle import codec_oracle as O
+    ov = O.VARIANTS["model_0"]
+    enc = O.init_params(ov["enc"], 3, 1234, "fanin")
+    dec = O.condition_decoder("model_0", O.init_params(ov["dec"], ov["bottleneck"], 1235, "fanin"), 2)
+    image = O.synthetic_image(256, 384, 7)
+    with T.Codec("model_0", quan_scale=2, mean=MEAN, std=STD, enc_params=enc, dec_params=dec, compute=compute) as c:
+        c.hist_reset()
+        rec, sym = c.roundtrip_images(image[None], 128)
+        counts = c.hist_read()
+    s_ref, r_ref = O.codec_roundtrip(image, "model_0", enc, dec, MEAN, STD, 2, 128)
+    cum = entry.cum_freq_table(counts / counts.sum(), 4096)
+    sizes = []
+    with tempfile.TemporaryDirectory() as d:
+        for k, stream in enumerate((sym[0].reshape(-1), s_ref.reshape(-1).astype(np.uint8))):
+            e = range_coder.RangeEncoder(os.path.join(d, f"{k}.bin"))
+            e.encode(stream, cum)
+            e.close()
+            sizes.append(os.path.getsize(os.path.join(d, f"{k}.bin")))
+    px = image.shape[0] * image.shape[1]
+    diff = np.abs(rec[0].astype(int) - r_ref.astype(int))
+    return {"sample": "one 256x384 synthetic image, model_0, fan-in weights, 6 patches",
+            "symbols": int(s_ref.size), "symbol_mismatches": int((sym[0].reshape(s_ref.shape) != s_ref).sum()),
+            "recon_max_abs_diff_u8": int(diff.max()), "recon_pixels_differing": int((diff != 0).sum()),
+            "bpp": 8.0 * sizes[0] / px, "bpp_delta": 8.0 * (sizes[0] - sizes[1]) / px,
+            "psnr_db": float(entry.psnr([image], [rec[0]])),
+            "psnr_delta_db": float(entry.psnr([image], [rec[0]]) - entry.psnr([image], [r_ref]))}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -347,6 +382,9 @@ def run_b200(args):
                "sample": f"{args.cpu_images} of the {B} 2048x1536 images (192 patches each), best of 3; torch-CPU fp32 "
                          "oracle restatement (TensorFlow not installable)"}
 
+    parity = None
+    if cpu is not None and VARIANT == "model_0":
+        parity = parity_sample(compute)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -368,6 +406,7 @@ def run_b200(args):
             "gpu_launches": int(launches) * world,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity": parity,
         }
         print(json.dumps(line), flush=True)
     codec.close()

@@ -87,6 +87,11 @@ const char* tic_create_error(void);
 /* Run on the caller's CUDA stream (cudaStream_t as void*); default: a private stream. */
 int tic_set_stream(tic_codec* h, void* cuda_stream);
 int tic_set_compute_mode(tic_codec* h, int mode);
+/* Synchronises the handle's stream and returns its sticky status: TIC_OK, or TIC_ERR_UNSUPPORTED once a
+ * TIC_COMPUTE_TENSOR_F16X3 run produced an activation outside the fp16 range (|x| >= 65504: every kernel that writes
+ * fp16 pair planes checks).  Host-buffer calls return the status themselves; device-buffer calls are asynchronous, so
+ * the status shows at the next hot-path call or here.  tic_set_compute_mode clears it. */
+int tic_check_status(tic_codec* h);
 /* Patches pushed through the layer stack per launch sequence (workspace size).
  * Given in units of 128x128 patches; scaled by (128/P)^2 for other patch sizes. */
 int tic_set_chunk_patches(tic_codec* h, int chunk);
@@ -162,6 +167,30 @@ int tic_hist_device_ptr(tic_codec* h, void** dev_ptr);
  * sums[h_b*w_b*c_b] (uint64) += sum_n symbols[n, pos].  symbols u8 [n, npos]. */
 int tic_position_sums(tic_codec* h, const uint8_t* symbols, int64_t n, int64_t npos,
                       uint64_t* sums, int mem);
+/* The same per sess.run batch: sums[b][pos] = sum over patches [b*batch, (b+1)*batch) (overwritten, not accumulated),
+ * b < ceil(n / batch).  The reference folds one batch of 64 at a time into a float64 running mean
+ * (cal_encoded_distribution.py:111-128); exact integer batch sums let the host repeat that arithmetic bit for bit. */
+int tic_position_sums_batched(tic_codec* h, const uint8_t* symbols, int64_t n, int64_t npos, int64_t batch,
+                              uint64_t* sums, int mem);
+
+/* ---- GPU entropy stage ----------------------------- */
+/* The per-image static-model range coder of encode.py:171-202 (RangeEncoder(path).encode(seq, cum_freq); close()) on
+ * the device: n_streams streams of stream_len uint8 symbols each (one image's patch-major symbol sequence,
+ * encode.py:171-182, exactly what tic_encode_images leaves in HBM), one table for all (encode.py:76-91).  Stream i is
+ * written to out + i * out_stride (tic_entropy_bound(stream_len) bytes always suffice), out_bytes[i] = its stored
+ * length.  The bytes are IDENTICAL to what the host coder (include/tic_rangecoder.h) writes to its file for the same
+ * symbols and table: both compile include/tic_rc_core.h.  Tables: 1..256 symbols, total <= 65536.
+ * mem = TIC_MEM_DEVICE: symbols / out / out_bytes are device buffers, asynchronous on the handle's stream (errors —
+ * a symbol outside the table or of zero probability — surface through tic_check_status); cum_freq is always a host
+ * array.  mem = TIC_MEM_HOST: staged, synchronous, only the stored bytes are copied back. */
+int64_t tic_entropy_bound(int64_t stream_len);
+int tic_entropy_encode(tic_codec* h, const uint8_t* symbols, int64_t n_streams, int64_t stream_len, const uint32_t* cum_freq,
+                       int n_cum, uint8_t* out, int64_t out_stride, int64_t* out_bytes, int mem);
+/* RangeDecoder(path).decode(n, cum_freq) (decode.py:79-101, 182) for n_streams files at once: stream i = in_bytes[i]
+ * stored bytes at in + i * in_stride (in_stride a multiple of 16, device buffers 16-byte aligned; bytes past the stored
+ * length read as zero, like the host decoder past EOF) -> symbols[i * stream_len ...]. */
+int tic_entropy_decode(tic_codec* h, const uint8_t* in, int64_t n_streams, int64_t in_stride, const int64_t* in_bytes,
+                       const uint32_t* cum_freq, int n_cum, uint8_t* symbols, int64_t stream_len, int mem);
 
 /* ---- introspection (measurement) ----------------------------------------- */
 /* Kernels launched by this handle since creation (bench.py's gpu_launches). */

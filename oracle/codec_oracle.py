@@ -409,17 +409,25 @@ def symbol_histogram(symbols, quan_scale):
 
 
 def position_mean(symbol_batches):
-    """cal_encoded_distribution.py:111-149: running mean over patches of every bottleneck position;
-    returns (mean per position, [1-p, p] rows, argsort order)."""
+    """cal_encoded_distribution.py:111-149, literally: the fetched batches are float32 tensors; the running mean is
+    float64 (np.zeros), the per-batch term is np.sum(float32 batch, axis=0) / n evaluated in float32 (:126-128);
+    one_prob = np.mean(seq_prob), prob = [1 - one_prob, one_prob] (:144-145); encoded_order = sorted(range(len), key =
+    seq_prob[k]) — a stable sort (:149).  Returns (seq_prob, prob, encoded_order)."""
     n = 0
-    mean = 0.0
+    seq_prob = None
     for b in symbol_batches:
-        b = np.asarray(b, dtype=np.float64).reshape(len(b), -1)
-        prev = n
-        n += b.shape[0]
-        mean = mean * (1.0 * prev / n) + np.sum(b, axis=0) / n
-    prob = np.stack([1.0 - mean, mean], axis=1)
-    return mean, prob, np.argsort(mean)
+        encoded_output = np.asarray(b, dtype=np.float32)
+        batch_num = encoded_output.shape[0]
+        if seq_prob is None:
+            seq_prob = np.zeros(int(np.prod(encoded_output.shape[1:])))
+        prev_n = n
+        n += batch_num
+        encoded_seq = np.reshape(encoded_output, (batch_num, -1))
+        seq_prob = seq_prob * (1.0 * prev_n / n) + np.sum(encoded_seq, axis=0) / n
+    one_prob = np.mean(seq_prob)
+    prob = [1.0 - one_prob, one_prob]
+    encoded_order = sorted(range(len(seq_prob)), key=lambda k: seq_prob[k])
+    return seq_prob, np.asarray(prob), encoded_order
 
 
 def coder_table(prob, resolution, prob_to_cum_freq):

@@ -206,8 +206,12 @@ def test_histogram_position_mean_and_metrics():
     freq = O.symbol_histogram(sym, 2)
     assert freq.sum() == sym.size and freq[1] == sym.sum()
     mean, prob, order = O.position_mean([sym[:4], sym[4:]])
-    np.testing.assert_allclose(mean, sym.reshape(10, -1).mean(0), atol=1e-12)
-    assert prob.shape == (256, 2) and np.allclose(prob.sum(1), 1)
+    np.testing.assert_allclose(mean, sym.reshape(10, -1).mean(0), atol=1e-7)  # float32 batch terms (cal_encoded_distribution.py:128)
+    # [1 - p, p] of the mean over positions (:144-145) and the stable position order (:149)
+    assert prob.shape == (2,) and np.isclose(prob.sum(), 1) and np.isclose(prob[1], sym.mean(), atol=1e-7)
+    assert sorted(order) == list(range(256)) and all(mean[order[i]] <= mean[order[i + 1]] for i in range(255))
+    ties = [k for k in range(255) if mean[order[k]] == mean[order[k + 1]]]
+    assert ties and all(order[k] < order[k + 1] for k in ties)  # stable: ties keep position order
     a = np.zeros((4, 4, 3), np.uint8)
     b = np.full((4, 4, 3), 1, np.uint8)
     assert abs(O.psnr([(a, b)]) - 20 * np.log10(255.0)) < 1e-9

@@ -95,6 +95,69 @@ def test_binary_symbols_reach_the_entropy(tmp_path):
     assert np.array_equal(dec.decode(sym.size, cum, dtype=np.uint8), sym)
 
 
+def test_streams_batch_equals_the_file_coder(tmp_path):
+    """encode_streams (thread pool, in memory) writes exactly the bytes RangeEncoder(path).encode(...); close() writes;
+    decode_streams reads them back; every thread count gives the same bytes."""
+    rs = np.random.RandomState(12)
+    for k, total in ((2, 4096), (2, 3000), (7, 1000), (256, 65536)):
+        p = rs.dirichlet([0.4] * k)
+        cum = RC.prob_to_cum_freq(p * 0.99 + 0.01 / k, resolution=total)
+        streams = [rs.choice(k, size=n, p=p).astype(np.uint8) for n in (0, 1, 17, 4096, 30001)]
+        blobs = RC.encode_streams(streams, cum, threads=3)
+        assert blobs == RC.encode_streams(streams, cum, threads=1)
+        for i, (s, b) in enumerate(zip(streams, blobs)):
+            path = tmp_path / f"s{k}_{i}.bin"
+            e = RC.RangeEncoder(str(path))
+            e.encode(s, cum)
+            e.close()
+            assert path.read_bytes() == b and e.bytes_written == len(b)
+            assert len(b) <= RC.load().tic_rc_max_encoded_bytes(len(s))
+        back = RC.decode_streams(blobs, [len(s) for s in streams], cum, threads=2)
+        assert all(np.array_equal(a, b) for a, b in zip(back, streams))
+    # a 2-D array is one stream per row
+    sym = (rs.rand(5, 1000) < 0.3).astype(np.uint8)
+    assert RC.encode_streams(sym, [0, 2800, 4096]) == RC.encode_streams(list(sym), [0, 2800, 4096])
+
+
+def test_carry_propagation_and_stream_tail(tmp_path):
+    """Long runs of a near-certain symbol park 0xFF bytes behind the cache byte; a rare symbol then carries through
+    them.  Round trips at extreme skews and totals, empty streams store nothing, trailing zero bytes are not stored."""
+    rs = np.random.RandomState(3)
+    for cum in ([0, 65535, 65536], [0, 1, 65536], [0, 4095, 4096], [0, 1, 2], [0, 255, 256, 65536]):
+        k = len(cum) - 1
+        w = np.diff(cum) / cum[-1]
+        for n in (1, 2, 3, 1000, 50000):
+            s = rs.choice(k, size=n, p=w).astype(np.uint8)
+            if n >= 1000:
+                s[rs.randint(0, n, size=5)] = int(np.argmin(w))  # force the rare symbol in
+            b, = RC.encode_streams([s], cum)
+            assert np.array_equal(RC.decode_streams([b], [n], cum)[0], s), (cum, n)
+            assert not b or b[-1] != 0  # trailing zeros are implied, never stored
+    assert RC.encode_streams([np.zeros(0, np.uint8)], [0, 1, 2]) == [b""]
+    # the all-zeros code value: a stream of the first symbol under a dyadic table stores nothing at all
+    assert RC.encode_streams([np.zeros(64, np.uint8)], [0, 2, 4]) == [b""]
+    assert np.array_equal(RC.decode_streams([b""], [64], [0, 2, 4])[0], np.zeros(64, np.uint8))
+    # totals above 2^16 are rejected (include/tic_rc_core.h), like any invalid table
+    with pytest.raises(ValueError):
+        RC.encode_streams([np.zeros(4, np.uint8)], [0, 1, 65537])
+    e = RC.RangeEncoder(str(tmp_path / "t.bin"))
+    with pytest.raises(ValueError):
+        e.encode([0, 1], [0, 40000, 80000])
+    e.close()
+
+
+def test_rangecoder_library_exports_every_declared_symbol():
+    import ctypes
+    import re
+    from tf_image_compression_b200 import _lib as L
+    header = (ROOT / "include" / "tic_rangecoder.h").read_text()
+    declared = set(re.findall(r"\b(tic_rc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(RC._SIG), declared ^ set(RC._SIG)
+    lib = ctypes.CDLL(str(L.RC_LIB_PATH))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
 def test_prob_to_cum_freq_invariants():
     rs = np.random.RandomState(190)
     p0 = rs.dirichlet([0.1] * 50)

@@ -53,6 +53,13 @@ SIGNATURES = {
     "tic_hist_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "tic_hist_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "tic_position_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
+    "tic_position_sums_batched": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int]),
+    "tic_check_status": (C.c_int, [C.c_void_p]),
+    "tic_entropy_bound": (C.c_int64, [C.c_int64]),
+    "tic_entropy_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_int]),
+    "tic_entropy_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_int64, C.c_int]),
     "tic_launch_count": (C.c_int64, [C.c_void_p]),
     "tic_last_kernel_ms": (C.c_float, [C.c_void_p]),
     "tic_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

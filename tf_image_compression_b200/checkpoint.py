@@ -28,7 +28,6 @@ from pathlib import Path
 
 import numpy as np
 
-from . import _lib as L
 
 MAGIC = 0xDB4775248B80FB57
 _DTYPES = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 6: np.int8, 9: np.int64, 10: np.bool_,
@@ -41,9 +40,10 @@ class CheckpointError(ValueError):
 
 
 def crc32c(data) -> int:
-    """CRC-32C (Castagnoli) through the C ABI (tic_crc32c)."""
-    b = bytes(data) if not isinstance(data, (bytes, bytearray)) else data
-    return int(L.load().tic_crc32c(b, len(b)))
+    """CRC-32C (Castagnoli) of any bytes-like object through the host-only library (tic_rc_crc32c in
+    librangecoder.so: reading a checkpoint never needs the CUDA library)."""
+    from . import range_coder
+    return range_coder.crc32c(data)
 
 
 def masked_crc32c(data) -> int:
@@ -255,9 +255,10 @@ def read_checkpoint(prefix, names=None, verify=True):
         count = int(np.prod(e["shape"], dtype=np.int64)) if e["shape"] else 1
         if raw.size != e["size"] or count * dt.itemsize != e["size"]:
             raise CheckpointError(f"{name}: {e['size']} bytes on record, shape {e['shape']} {dt} needs {count * dt.itemsize}")
-        if verify and e["crc32c"] is not None and masked_crc32c(raw.tobytes()) != e["crc32c"]:
+        rb = raw.tobytes()
+        if verify and e["crc32c"] is not None and masked_crc32c(rb) != e["crc32c"]:
             raise CheckpointError(f"{name}: crc32c mismatch in the data shard")
-        out[name] = np.frombuffer(raw.tobytes(), dtype=dt).reshape(e["shape"]).copy()
+        out[name] = np.frombuffer(rb, dtype=dt).reshape(e["shape"]).copy()
     return out
 
 

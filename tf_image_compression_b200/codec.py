@@ -199,6 +199,13 @@ class Codec:
         self._check(self.lib.tic_bottleneck_shape(self._h, int(patch_size), C.byref(hb), C.byref(wb), C.byref(cb)))
         return hb.value, wb.value, cb.value
 
+    @staticmethod
+    def _expect_shape(what, x, shape):
+        """The C side reads / writes exactly prod(shape) elements: a wrong-sized caller buffer must be a ValueError
+        here, never an out-of-bounds access there."""
+        if tuple(int(v) for v in x.shape) != tuple(int(v) for v in shape):
+            raise ValueError(f"{what} must have shape {tuple(shape)}, got {tuple(x.shape)}")
+
     def _alloc_like(self, ref, shape, dtype):
         if _is_torch(ref):
             tdt = {np.uint8: torch.uint8, np.float32: torch.float32}[dtype]
@@ -218,6 +225,7 @@ class Codec:
             out = self._alloc_like(patches, (n, hb, wb, cb), out_dtype)
         else:
             out_dtype = np.uint8 if str(out.dtype).endswith("uint8") else np.float32
+            self._expect_shape("out", out, (n, hb, wb, cb))
         dst = _Buf(out, out_dtype, self.device)
         if dst.mem != src.mem:
             raise ValueError("input and output must both be host or both be device buffers")
@@ -234,8 +242,12 @@ class Codec:
         P = int(patch_size)
         hb, wb, cb = self.bottleneck_shape(P)
         gh, gw = -(-H // P), -(-W // P)
+        if tuple(images.shape[3:]) != (3,):
+            raise ValueError(f"images must be [B,H,W,3], got {tuple(images.shape)}")
         if out is None:
             out = self._alloc_like(images, (B, gh * gw, hb, wb, cb), np.uint8)
+        else:
+            self._expect_shape("out", out, (B, gh * gw, hb, wb, cb))
         dst = _Buf(out, np.uint8, self.device)
         if dst.mem != src.mem:
             raise ValueError("input and output must both be host or both be device buffers")
@@ -254,8 +266,12 @@ class Codec:
             if l.kind == "c":
                 down *= l.stride
         P = hb * up // down
+        if hb != wb:
+            raise ValueError(f"symbol maps must be square, got {hb}x{wb}")
         if out is None:
             out = self._alloc_like(symbols, (n, P, P, 3), np.float32)
+        else:
+            self._expect_shape("out", out, (n, P, P, 3))
         dst = _Buf(out, np.float32, self.device)
         if dst.mem != src.mem:
             raise ValueError("input and output must both be host or both be device buffers")
@@ -266,17 +282,22 @@ class Codec:
         """decoder + concat_patches (+ np.around -> uint8) fused: symbols [B, gh*gw, hb, wb, cb] uint8 ->
         [B,H,W,3] uint8 (rounded) or float32."""
         B = int(symbols.shape[0])
+        gh, gw = -(-int(height) // int(patch_size)), -(-int(width) // int(patch_size))
+        # exactly the bottleneck shape this variant produces for this patch size (the C side reads
+        # gh*gw*hb*wb*cb bytes per image unconditionally: files of another variant / patch size must fail here)
+        hb, wb, cb = self.bottleneck_shape(int(patch_size))
+        if cb != self.dec_layers[0].cin:
+            raise ValueError(f"decoder expects {self.dec_layers[0].cin} symbol channels, the encoder graph produces {cb}")
+        self._expect_shape("symbols", symbols, (B, gh * gw, hb, wb, cb))
         src = _Buf(symbols, np.uint8, self.device, self)
         if out is None:
             out = self._alloc_like(symbols, (B, int(height), int(width), 3), out_dtype)
         else:
             out_dtype = np.uint8 if str(out.dtype).endswith("uint8") else np.float32
+            self._expect_shape("out", out, (B, int(height), int(width), 3))
         dst = _Buf(out, out_dtype, self.device)
         if dst.mem != src.mem:
             raise ValueError("input and output must both be host or both be device buffers")
-        gh, gw = -(-int(height) // int(patch_size)), -(-int(width) // int(patch_size))
-        if int(np.prod(symbols.shape[1:])) % (gh * gw) != 0:
-            raise ValueError("symbol count per image is not a multiple of the patch grid")
         self._check(self.lib.tic_decode_images(self._h, src.ptr, B, int(height), int(width), int(patch_size), dst.ptr,
                                                L.U8 if out_dtype == np.uint8 else L.F32, src.mem))
         return out
@@ -292,13 +313,18 @@ class Codec:
         P = int(patch_size)
         hb, wb, cb = self.bottleneck_shape(P)
         gh, gw = -(-H // P), -(-W // P)
+        if tuple(images.shape[3:]) != (3,):
+            raise ValueError(f"images must be [B,H,W,3], got {tuple(images.shape)}")
         if out is None:
             out = self._alloc_like(images, (B, H, W, 3), out_dtype)
         else:
             out_dtype = np.uint8 if str(out.dtype).endswith("uint8") else np.float32
+            self._expect_shape("out", out, (B, H, W, 3))
         dst = _Buf(out, out_dtype, self.device)
         if out_symbols is None and (want_symbols or src.mem == L.MEM_DEVICE):
             out_symbols = self._alloc_like(images, (B, gh * gw, hb, wb, cb), np.uint8)
+        elif out_symbols is not None:
+            self._expect_shape("out_symbols", out_symbols, (B, gh * gw, hb, wb, cb))
         sym = _Buf(out_symbols, np.uint8, self.device) if out_symbols is not None else None
         if dst.mem != src.mem or (sym is not None and sym.mem != src.mem):
             raise ValueError("input and outputs must all be host or all be device buffers")
@@ -311,9 +337,13 @@ class Codec:
         if self.post_layers is None:
             raise TicError("post-filter not configured (set_postfilter)")
         n, P = int(tiles.shape[0]), int(tiles.shape[1])
+        if tuple(tiles.shape[1:]) != (P, P, 3):
+            raise ValueError(f"tiles must be [N,P,P,3], got {tuple(tiles.shape)}")
         src = _Buf(tiles, np.float32, self.device, self)
         if out is None:
             out = self._alloc_like(tiles, tuple(tiles.shape), np.float32)
+        else:
+            self._expect_shape("out", out, tuple(tiles.shape))
         dst = _Buf(out, np.float32, self.device)
         self._check(self.lib.tic_postfilter_patches(self._h, src.ptr, n, P, dst.ptr, src.mem))
         return out
@@ -347,6 +377,8 @@ class Codec:
         src = _Buf(x, np.float32, self.device, self)
         if out is None:
             out = self._alloc_like(x, tuple(x.shape), np.uint8)
+        else:
+            self._expect_shape("out", out, tuple(x.shape))
         dst = _Buf(out, np.uint8, self.device)
         n = int(np.prod(x.shape))
         self._check(self.lib.tic_round_u8(self._h, src.ptr, dst.ptr, n, src.mem))
@@ -378,6 +410,71 @@ class Codec:
         ptr = sums.data_ptr() if _is_torch(sums) else sums.ctypes.data
         self._check(self.lib.tic_position_sums(self._h, src.ptr, n, npos, ptr, src.mem))
         return sums
+
+    def position_sums_batched(self, symbols, batch=64):
+        """Exact per-batch integer sums [ceil(n/batch), hb*wb*cb] (uint64): what one sess.run batch contributes to the
+        reference's running mean (cal_encoded_distribution.py:111-128, batch_size = 64 at :92)."""
+        n = int(symbols.shape[0])
+        npos = int(np.prod(symbols.shape[1:]))
+        nb = -(-n // int(batch))
+        src = _Buf(symbols, np.uint8, self.device, self)
+        sums = (torch.zeros((nb, npos), dtype=torch.int64, device=symbols.device) if _is_torch(symbols)
+                else np.zeros((nb, npos), dtype=np.uint64))
+        if n:
+            ptr = sums.data_ptr() if _is_torch(sums) else sums.ctypes.data
+            self._check(self.lib.tic_position_sums_batched(self._h, src.ptr, n, npos, int(batch), ptr, src.mem))
+        return sums
+
+    # ---- GPU entropy stage ----------------------------------------------------------------------
+    def entropy_bound(self, stream_len):
+        return int(self.lib.tic_entropy_bound(int(stream_len)))
+
+    def entropy_encode(self, symbols, cum_freq):
+        """encode.py:171-202 on the device: symbols [n_streams, ...] uint8 (one image's patch-major symbol sequence per
+        row, e.g. the result of encode_images) -> (out uint8 [n_streams, bound], nbytes int64 [n_streams]); stream i is
+        out[i, :nbytes[i]], byte-identical to range_coder.RangeEncoder(path).encode(symbols[i].reshape(-1), cum_freq);
+        close().  Device tensors stay on the device (asynchronous; errors surface through check_status())."""
+        n = int(symbols.shape[0])
+        slen = int(np.prod(symbols.shape[1:])) if n else 0
+        src = _Buf(symbols, np.uint8, self.device, self)
+        cum = np.ascontiguousarray(np.asarray([int(v) for v in cum_freq], dtype=np.uint32))
+        stride = self.entropy_bound(slen)
+        out = self._alloc_like(symbols, (n, stride), np.uint8)
+        nbytes = (torch.zeros(n, dtype=torch.int64, device=symbols.device) if _is_torch(symbols) else np.zeros(n, dtype=np.int64))
+        dst = _Buf(out, np.uint8, self.device)
+        nb_ptr = nbytes.data_ptr() if _is_torch(nbytes) else nbytes.ctypes.data
+        self._check(self.lib.tic_entropy_encode(self._h, src.ptr, n, slen, cum.ctypes.data, cum.size, dst.ptr, stride, nb_ptr, src.mem))
+        return out, nbytes
+
+    def entropy_decode(self, streams, nbytes, stream_len, cum_freq, out=None):
+        """decode.py:79-101,182 on the device: streams uint8 [n_streams, stride] (stride a multiple of 16) holding
+        nbytes[i] stored bytes each -> symbols uint8 [n_streams, stream_len]."""
+        n, stride = int(streams.shape[0]), int(streams.shape[1])
+        src = _Buf(streams, np.uint8, self.device, self)
+        cum = np.ascontiguousarray(np.asarray([int(v) for v in cum_freq], dtype=np.uint32))
+        if _is_torch(streams):
+            nb = nbytes.to(device=streams.device, dtype=torch.int64).contiguous()
+            nb_ptr = nb.data_ptr()
+        else:
+            nb = np.ascontiguousarray(np.asarray(nbytes, dtype=np.int64))
+            nb_ptr = nb.ctypes.data
+        if int(nb.shape[0]) != n:
+            raise ValueError("nbytes must have one entry per stream")
+        if out is None:
+            out = self._alloc_like(streams, (n, int(stream_len)), np.uint8)
+        else:
+            self._expect_shape("out", out.reshape(n, -1) if n else out, (n, int(stream_len)))
+        dst = _Buf(out, np.uint8, self.device)
+        if dst.mem != src.mem:
+            raise ValueError("input and output must both be host or both be device buffers")
+        self._check(self.lib.tic_entropy_decode(self._h, src.ptr, n, stride, nb_ptr, cum.ctypes.data, cum.size, dst.ptr,
+                                                int(stream_len), src.mem))
+        return out
+
+    def check_status(self):
+        """Synchronise the codec's stream and raise if a tensor-mode ('f16x3') run left the fp16 range (|activation| >=
+        65504): device-buffer calls are asynchronous, so their status surfaces here or at the next call."""
+        self._check(self.lib.tic_check_status(self._h))
 
     # ---- measurement ---------------------------------------------------------------------------
     @property

@@ -1,183 +1,185 @@
-// Host entropy coder behind include/tic_rangecoder.h: integer arithmetic coding with 32-bit code values
-// (the published "low / high / underflow bits" scheme), static cumulative-frequency tables supplied per
-// call, MSB-first bit stream.  The decoder zero-extends the stream past EOF, which lets close() write the
-// shortest tail whose zero extension lies inside the final interval (for a dyadic source that ends on a
-// byte boundary: nothing, so the reference's known-answer vector is exactly one byte per 8 bits).
+// Host entropy coder behind include/tic_rangecoder.h.  The arithmetic lives in include/tic_rc_core.h (single source
+// with the CUDA entropy stage): a carry-propagating byte-wise range coder, static cumulative-frequency tables supplied
+// per call.  This file adds files, buffers, table checks, whole-stream batches on a thread pool, prob_to_cum_freq and
+// the CRC-32C of the checkpoint reader (host-only, so reading a checkpoint never needs the CUDA library).
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "../../include/tic_rangecoder.h"
+#include "../../include/tic_rc_core.h"
 
 namespace {
-
-constexpr uint64_t kMax = 0xFFFFFFFFull;       // largest code value
-constexpr uint64_t kQuarter = 0x40000000ull;
-constexpr uint64_t kHalf = 0x80000000ull;
-constexpr uint64_t kThreeQuarters = 0xC0000000ull;
-constexpr uint64_t kMaxTotal = kQuarter;       // frequency totals above this lose the decodability guarantee
 
 int check_table(const uint32_t* cum, int n_cum) {
   if (!cum || n_cum < 2) return TIC_RC_ERR_TABLE;  // [] and [0] are invalid tables
   if (cum[0] != 0) return TIC_RC_ERR_TABLE;
   for (int i = 1; i < n_cum; ++i)
     if (cum[i] < cum[i - 1]) return TIC_RC_ERR_TABLE;
-  if (cum[n_cum - 1] == 0 || (uint64_t)cum[n_cum - 1] > kMaxTotal) return TIC_RC_ERR_TABLE;
+  if (cum[n_cum - 1] == 0 || cum[n_cum - 1] > TIC_RC_MAX_TOTAL) return TIC_RC_ERR_TABLE;
   return TIC_RC_OK;
+}
+
+inline bool is_pow2(uint32_t v) { return (v & (v - 1)) == 0; }
+inline int log2u(uint32_t v) {
+  int k = 0;
+  while ((1u << k) < v) ++k;
+  return k;
+}
+
+// Byte sink that does not store the trailing zero bytes of the stream: zeros are counted and only written once a
+// non-zero byte follows them.
+struct FileSink {
+  FILE* f = nullptr;
+  std::vector<uint8_t> buf;
+  uint64_t zrun = 0;
+  int64_t stored = 0;
+  bool io_error = false;
+  void raw(uint8_t b) {
+    buf.push_back(b);
+    ++stored;
+    if (buf.size() >= (1u << 16)) flush();
+  }
+  void put(uint8_t b) {
+    if (b == 0) {
+      ++zrun;
+      return;
+    }
+    for (; zrun > 0; --zrun) raw(0);
+    raw(b);
+  }
+  void flush() {
+    if (!buf.empty() && f) {
+      if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) io_error = true;
+    }
+    buf.clear();
+  }
+};
+
+// Sink into caller memory; `len` ends after the last non-zero byte (bytes are written as they come, so zeros inside
+// the stream are in place and the trailing ones are simply not counted).
+struct MemSink {
+  uint8_t* p;
+  int64_t cap, pos = 0, len = 0;
+  bool overflow = false;
+  MemSink(uint8_t* p_, int64_t cap_) : p(p_), cap(cap_) {}
+  void put(uint8_t b) {
+    if (pos >= cap) {
+      overflow = true;
+      return;
+    }
+    p[pos++] = b;
+    if (b) len = pos;
+  }
+};
+
+struct FileSource {
+  FILE* f = nullptr;
+  std::vector<uint8_t> buf;
+  size_t pos = 0;
+  uint32_t get() {
+    if (pos >= buf.size()) {
+      buf.resize(1 << 16);
+      const size_t got = f ? fread(buf.data(), 1, buf.size(), f) : 0;
+      buf.resize(got);
+      pos = 0;
+      if (got == 0) return 0;  // zero extension past EOF
+    }
+    return buf[pos++];
+  }
+};
+
+struct MemSource {
+  const uint8_t* p;
+  int64_t n, pos = 0;
+  MemSource(const uint8_t* p_, int64_t n_) : p(p_), n(n_) {}
+  uint32_t get() { return pos < n ? p[pos++] : 0u; }
+};
+
+template <typename T, class Sink>
+int encode_symbols(tic_rc_enc_state* st, Sink& out, const T* sym, int64_t n, const uint32_t* cum, int n_cum) {
+  const uint32_t total = cum[n_cum - 1];
+  const int64_t nsym = n_cum - 1;
+  const bool p2 = is_pow2(total);
+  const int k = p2 ? log2u(total) : 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t s = (int64_t)sym[i];
+    if (s < 0 || s >= nsym) return TIC_RC_ERR_SYMBOL;
+    const uint32_t lo = cum[s], hi = cum[s + 1];
+    if (hi == lo) return TIC_RC_ERR_SYMBOL;  // symbols with zero probability cannot be encoded
+    const uint32_t r = p2 ? st->range >> k : st->range / total;
+    tic_rc_enc_step(st, out, r, lo, hi);
+  }
+  return TIC_RC_OK;
+}
+
+template <typename T, class Source>
+int decode_symbols(tic_rc_dec_state* st, Source& in, T* out, int64_t n, const uint32_t* cum, int n_cum) {
+  tic_rc_dec_prime(st, in);
+  const uint32_t total = cum[n_cum - 1];
+  const bool p2 = is_pow2(total);
+  const int k = p2 ? log2u(total) : 0;
+  if (n_cum == 3) {
+    // binary alphabet (every shipped config: quan_scale = 2): one compare instead of the division and the search
+    const uint32_t c1 = cum[1];
+    for (int64_t i = 0; i < n; ++i) {
+      const uint32_t r = p2 ? st->range >> k : st->range / total;
+      const uint32_t t = r * c1;
+      // zero-width symbols: c1 == 0 -> always 1; c1 == total -> 1 only for corrupt streams (clamped to 0)
+      const bool one = c1 == total ? false : st->code >= t;
+      out[i] = (T)(one ? 1 : 0);
+      tic_rc_dec_step(st, in, r, one ? c1 : 0u, one ? total : c1);
+    }
+    return TIC_RC_OK;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    const uint32_t r = p2 ? st->range >> k : st->range / total;
+    const uint32_t v = tic_rc_dec_target(st, r, total);
+    // last entry with cum[s] <= v (skips zero-width symbols)
+    const uint32_t* it = std::upper_bound(cum, cum + n_cum, v);
+    const int64_t s = (it - cum) - 1;
+    out[i] = (T)s;
+    tic_rc_dec_step(st, in, r, cum[s], cum[s + 1]);
+  }
+  return TIC_RC_OK;
+}
+
+template <class Fn>
+void parallel_for(int64_t n, int n_threads, Fn fn) {
+  if (n_threads <= 0) n_threads = (int)std::thread::hardware_concurrency();
+  n_threads = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n));
+  if (n_threads == 1) {
+    for (int64_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int64_t> next{0};
+  std::vector<std::thread> pool;
+  pool.reserve(n_threads);
+  for (int t = 0; t < n_threads; ++t)
+    pool.emplace_back([&] {
+      for (;;) {
+        const int64_t i = next.fetch_add(1);
+        if (i >= n) break;
+        fn(i);
+      }
+    });
+  for (auto& th : pool) th.join();
 }
 
 }  // namespace
 
 struct tic_rc_encoder {
-  FILE* f = nullptr;
-  uint64_t low = 0, high = kMax;
-  uint64_t pending = 0;
-  uint8_t cur = 0;
-  int nbits = 0;
-  int64_t bytes = 0;
-  std::vector<uint8_t> buf;
-  bool io_error = false;
-
-  void put_byte(uint8_t b) {
-    buf.push_back(b);
-    ++bytes;
-    if (buf.size() >= (1u << 16)) flush_buf();
-  }
-  void flush_buf() {
-    if (!buf.empty() && f) {
-      if (fwrite(buf.data(), 1, buf.size(), f) != buf.size()) io_error = true;
-      buf.clear();
-    }
-  }
-  void put_bit(int b) {
-    cur = (uint8_t)((cur << 1) | (b & 1));
-    if (++nbits == 8) {
-      put_byte(cur);
-      cur = 0;
-      nbits = 0;
-    }
-  }
-  void put_bit_plus_pending(int b) {
-    put_bit(b);
-    for (; pending > 0; --pending) put_bit(!b);
-  }
-  template <typename T>
-  int encode(const T* sym, int64_t n, const uint32_t* cum, int n_cum) {
-    const uint64_t total = cum[n_cum - 1];
-    const int64_t nsym = n_cum - 1;
-    for (int64_t i = 0; i < n; ++i) {
-      const int64_t s = (int64_t)sym[i];
-      if (s < 0 || s >= nsym) return TIC_RC_ERR_SYMBOL;
-      const uint64_t lo = cum[s], hi = cum[s + 1];
-      if (hi == lo) return TIC_RC_ERR_SYMBOL;  // symbols with zero probability cannot be encoded
-      const uint64_t range = high - low + 1;
-      high = low + range * hi / total - 1;
-      low = low + range * lo / total;
-      for (;;) {
-        if (high < kHalf) {
-          put_bit_plus_pending(0);
-        } else if (low >= kHalf) {
-          put_bit_plus_pending(1);
-        } else if (low >= kQuarter && high < kThreeQuarters) {
-          ++pending;
-          low -= kQuarter;
-          high -= kQuarter;
-        } else {
-          break;
-        }
-        high = ((high << 1) | 1) & kMax;
-        low = (low << 1) & kMax;
-      }
-    }
-    return TIC_RC_OK;
-  }
-  void terminate() {
-    if (pending > 0) {
-      // interval straddles the middle: one deciding bit plus the parked underflow bits
-      ++pending;
-      put_bit_plus_pending(low < kQuarter ? 0 : 1);
-    } else if (low != 0) {
-      // shortest prefix whose zero extension lies in [low, high]
-      for (int k = 1; k <= 32; ++k) {
-        const uint64_t unit = 1ull << (32 - k);
-        const uint64_t cand = (low + unit - 1) / unit * unit;
-        if (cand <= high) {
-          for (int b = 31; b >= 32 - k; --b) put_bit((int)((cand >> b) & 1));
-          break;
-        }
-      }
-    }
-    if (nbits > 0) {
-      put_byte((uint8_t)(cur << (8 - nbits)));
-      cur = 0;
-      nbits = 0;
-    }
-  }
+  tic_rc_enc_state st;
+  FileSink out;
 };
 
 struct tic_rc_decoder {
-  FILE* f = nullptr;
-  uint64_t low = 0, high = kMax, value = 0;
-  uint8_t cur = 0;
-  int nbits = 0;
-  bool primed = false;
-  std::vector<uint8_t> buf;
-  size_t pos = 0;
-
-  int get_bit() {
-    if (nbits == 0) {
-      if (pos >= buf.size()) {
-        buf.resize(1 << 16);
-        const size_t got = f ? fread(buf.data(), 1, buf.size(), f) : 0;
-        buf.resize(got);
-        pos = 0;
-      }
-      cur = pos < buf.size() ? buf[pos++] : 0;  // zero extension past EOF
-      nbits = 8;
-    }
-    --nbits;
-    return (cur >> nbits) & 1;
-  }
-  template <typename T>
-  int decode(T* out, int64_t n, const uint32_t* cum, int n_cum) {
-    if (!primed) {
-      for (int i = 0; i < 32; ++i) value = (value << 1) | (uint64_t)get_bit();
-      primed = true;
-    }
-    const uint64_t total = cum[n_cum - 1];
-    for (int64_t i = 0; i < n; ++i) {
-      const uint64_t range = high - low + 1;
-      uint64_t scaled = ((value - low + 1) * total - 1) / range;
-      if (scaled >= total) scaled = total - 1;  // corrupt stream: stay inside the table
-      // last entry with cum[s] <= scaled (skips zero-width symbols)
-      const uint32_t* it = std::upper_bound(cum, cum + n_cum, (uint32_t)scaled);
-      const int64_t s = (it - cum) - 1;
-      out[i] = (T)s;
-      const uint64_t lo = cum[s], hi = cum[s + 1];
-      high = low + range * hi / total - 1;
-      low = low + range * lo / total;
-      for (;;) {
-        if (high < kHalf) {
-        } else if (low >= kHalf) {
-          value -= kHalf;
-          low -= kHalf;
-          high -= kHalf;
-        } else if (low >= kQuarter && high < kThreeQuarters) {
-          value -= kQuarter;
-          low -= kQuarter;
-          high -= kQuarter;
-        } else {
-          break;
-        }
-        low <<= 1;
-        high = (high << 1) | 1;
-        value = ((value << 1) | (uint64_t)get_bit()) & kMax;
-      }
-    }
-    return TIC_RC_OK;
-  }
+  tic_rc_dec_state st;
+  FileSource in;
 };
 
 extern "C" {
@@ -188,34 +190,35 @@ int tic_rc_encoder_open(tic_rc_encoder** out, const char* path) {
   FILE* f = fopen(path, "wb");
   if (!f) return TIC_RC_ERR_IO;
   tic_rc_encoder* e = new tic_rc_encoder();
-  e->f = f;
+  tic_rc_enc_init(&e->st);
+  e->out.f = f;
   *out = e;
   return TIC_RC_OK;
 }
 
 int tic_rc_encode_u8(tic_rc_encoder* e, const uint8_t* symbols, int64_t n, const uint32_t* cum_freq, int n_cum) {
-  if (!e || !e->f) return TIC_RC_ERR_CLOSED;
+  if (!e || !e->out.f) return TIC_RC_ERR_CLOSED;
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return e->encode(symbols, n, cum_freq, n_cum);
+  return encode_symbols(&e->st, e->out, symbols, n, cum_freq, n_cum);
 }
 
 int tic_rc_encode_i32(tic_rc_encoder* e, const int32_t* symbols, int64_t n, const uint32_t* cum_freq, int n_cum) {
-  if (!e || !e->f) return TIC_RC_ERR_CLOSED;
+  if (!e || !e->out.f) return TIC_RC_ERR_CLOSED;
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return e->encode(symbols, n, cum_freq, n_cum);
+  return encode_symbols(&e->st, e->out, symbols, n, cum_freq, n_cum);
 }
 
 int tic_rc_encoder_close(tic_rc_encoder* e) {
   if (!e) return TIC_RC_ERR_CLOSED;
-  if (!e->f) return TIC_RC_OK;
-  e->terminate();
-  e->flush_buf();
-  const bool bad = e->io_error || fclose(e->f) != 0;
-  e->f = nullptr;
+  if (!e->out.f) return TIC_RC_OK;
+  tic_rc_enc_finish(&e->st, e->out);
+  e->out.flush();  // pending zeros are the stream's trailing zeros: not stored
+  const bool bad = e->out.io_error || fclose(e->out.f) != 0;
+  e->out.f = nullptr;
   return bad ? TIC_RC_ERR_IO : TIC_RC_OK;
 }
 
@@ -225,7 +228,7 @@ void tic_rc_encoder_free(tic_rc_encoder* e) {
   delete e;
 }
 
-int64_t tic_rc_encoder_bytes(const tic_rc_encoder* e) { return e ? e->bytes : 0; }
+int64_t tic_rc_encoder_bytes(const tic_rc_encoder* e) { return e ? e->out.stored : 0; }
 
 int tic_rc_decoder_open(tic_rc_decoder** out, const char* path) {
   if (!out || !path) return TIC_RC_ERR_IO;
@@ -233,32 +236,33 @@ int tic_rc_decoder_open(tic_rc_decoder** out, const char* path) {
   FILE* f = fopen(path, "rb");
   if (!f) return TIC_RC_ERR_IO;
   tic_rc_decoder* d = new tic_rc_decoder();
-  d->f = f;
+  tic_rc_dec_init(&d->st);
+  d->in.f = f;
   *out = d;
   return TIC_RC_OK;
 }
 
 int tic_rc_decode_u8(tic_rc_decoder* d, uint8_t* symbols, int64_t n, const uint32_t* cum_freq, int n_cum) {
-  if (!d || !d->f) return TIC_RC_ERR_CLOSED;
+  if (!d || !d->in.f) return TIC_RC_ERR_CLOSED;
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n_cum - 1 > 256) return TIC_RC_ERR_TABLE;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return d->decode(symbols, n, cum_freq, n_cum);
+  return decode_symbols(&d->st, d->in, symbols, n, cum_freq, n_cum);
 }
 
 int tic_rc_decode_i32(tic_rc_decoder* d, int32_t* symbols, int64_t n, const uint32_t* cum_freq, int n_cum) {
-  if (!d || !d->f) return TIC_RC_ERR_CLOSED;
+  if (!d || !d->in.f) return TIC_RC_ERR_CLOSED;
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return d->decode(symbols, n, cum_freq, n_cum);
+  return decode_symbols(&d->st, d->in, symbols, n, cum_freq, n_cum);
 }
 
 int tic_rc_decoder_close(tic_rc_decoder* d) {
   if (!d) return TIC_RC_ERR_CLOSED;
-  if (d->f) fclose(d->f);
-  d->f = nullptr;
+  if (d->in.f) fclose(d->in.f);
+  d->in.f = nullptr;
   return TIC_RC_OK;
 }
 
@@ -266,6 +270,44 @@ void tic_rc_decoder_free(tic_rc_decoder* d) {
   if (!d) return;
   tic_rc_decoder_close(d);
   delete d;
+}
+
+int64_t tic_rc_max_encoded_bytes(int64_t n_symbols) { return tic_rc_bound(n_symbols < 0 ? 0 : n_symbols); }
+
+int tic_rc_encode_streams(const uint8_t* symbols, const int64_t* sym_offsets, int64_t n_streams, const uint32_t* cum_freq,
+                          int n_cum, uint8_t* out, const int64_t* out_offsets, int64_t* out_bytes, int n_threads) {
+  int rc = check_table(cum_freq, n_cum);
+  if (rc != TIC_RC_OK) return rc;
+  if (n_streams < 0 || (n_streams > 0 && (!symbols || !sym_offsets || !out || !out_offsets || !out_bytes))) return TIC_RC_ERR_SYMBOL;
+  std::atomic<int> status{TIC_RC_OK};
+  parallel_for(n_streams, n_threads, [&](int64_t i) {
+    tic_rc_enc_state st;
+    tic_rc_enc_init(&st);
+    MemSink sink(out + out_offsets[i], out_offsets[i + 1] - out_offsets[i]);
+    int r = encode_symbols(&st, sink, symbols + sym_offsets[i], sym_offsets[i + 1] - sym_offsets[i], cum_freq, n_cum);
+    if (r == TIC_RC_OK) {
+      tic_rc_enc_finish(&st, sink);
+      if (sink.overflow) r = TIC_RC_ERR_IO;
+    }
+    out_bytes[i] = r == TIC_RC_OK ? sink.len : 0;
+    if (r != TIC_RC_OK) status.store(r);
+  });
+  return status.load();
+}
+
+int tic_rc_decode_streams(const uint8_t* in, const int64_t* in_offsets, const int64_t* in_bytes, int64_t n_streams,
+                          const uint32_t* cum_freq, int n_cum, uint8_t* symbols, const int64_t* sym_offsets, int n_threads) {
+  int rc = check_table(cum_freq, n_cum);
+  if (rc != TIC_RC_OK) return rc;
+  if (n_cum - 1 > 256) return TIC_RC_ERR_TABLE;
+  if (n_streams < 0 || (n_streams > 0 && (!in || !in_offsets || !in_bytes || !symbols || !sym_offsets))) return TIC_RC_ERR_SYMBOL;
+  parallel_for(n_streams, n_threads, [&](int64_t i) {
+    tic_rc_dec_state st;
+    tic_rc_dec_init(&st);
+    MemSource src(in + in_offsets[i], in_bytes[i]);
+    decode_symbols(&st, src, symbols + sym_offsets[i], sym_offsets[i + 1] - sym_offsets[i], cum_freq, n_cum);
+  });
+  return TIC_RC_OK;
 }
 
 int tic_rc_prob_to_cum_freq(const double* prob, int n, uint32_t resolution, uint32_t* cum_freq) {
@@ -320,6 +362,35 @@ int tic_rc_prob_to_cum_freq(const double* prob, int n, uint32_t resolution, uint
   cum_freq[0] = 0;
   for (int i = 0; i < n; ++i) cum_freq[i + 1] = cum_freq[i] + (uint32_t)freq[i];
   return TIC_RC_OK;
+}
+
+uint32_t tic_rc_crc32c(const void* data, uint64_t n) {
+  static uint32_t table[8][256];
+  static const bool ready = [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xffu];
+    return true;
+  }();
+  (void)ready;
+  const uint8_t* p = static_cast<const uint8_t*>(data);
+  uint32_t c = 0xffffffffu;
+  while (n >= 8) {  // slicing-by-8
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xffu] ^ table[6][(lo >> 8) & 0xffu] ^ table[5][(lo >> 16) & 0xffu] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xffu] ^ table[2][(hi >> 8) & 0xffu] ^ table[1][(hi >> 16) & 0xffu] ^ table[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ table[0][(c ^ *p++) & 0xffu];
+  return c ^ 0xffffffffu;
 }
 
 }  // extern "C"

@@ -14,6 +14,7 @@
 #include "tic_umma.cuh"
 #include "tic_umma16.cuh"
 #include "tic_first16.cuh"
+#include "tic_entropy.cuh"
 
 using namespace tic;
 
@@ -79,6 +80,11 @@ struct tic_codec {
   std::vector<float> prof_ms[3];
   std::vector<int64_t> prof_n[3];
   int num_sms = 148;
+  unsigned int* h_oflow = nullptr;  // host-mapped sticky flags: [0] a pair-plane split saw |x| >= 65504 (fp16 range),
+                                    // [1] entropy stage (1: symbol outside the table / of zero width, 2: slot too small)
+  unsigned int* d_oflow = nullptr;  // their device address
+  uint32_t* d_cum = nullptr;        // entropy stage: the call's cumulative-frequency table [257]
+  cudaEvent_t ev_switch = nullptr;  // orders the old stream before the new one in tic_set_stream
   std::string err;
 };
 
@@ -101,6 +107,32 @@ int fail(tic_codec* h, int code, const char* fmt, ...) {
       return fail((h), TIC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
+// Error paths of the staged (host-buffer) drivers: nothing may still be copying into / out of the caller's buffers
+// or the staging sets when the call returns.
+void quiesce(tic_codec* h) {
+  cudaStreamSynchronize(h->s_h2d);
+  cudaStreamSynchronize(h->stream);
+  cudaStreamSynchronize(h->s_d2h);
+}
+
+const char* kOverflowMsg =
+    "fp16-pair tensor mode: an activation reached the fp16 range limit (|x| >= 65504); results are invalid. "
+    "Use compute mode fp32 or 3xtf32 for these weights (tic_set_compute_mode clears the flag)";
+
+// Sticky fp16-range status: checked at the start of every hot-path call and after every call that synchronises.
+int overflow_status(tic_codec* h) {
+  if (h->h_oflow && *reinterpret_cast<volatile unsigned int*>(h->h_oflow)) return fail(h, TIC_ERR_UNSUPPORTED, "%s", kOverflowMsg);
+  if (h->h_oflow) {
+    const unsigned int es = *reinterpret_cast<volatile unsigned int*>(h->h_oflow + 1);
+    if (es) {
+      *reinterpret_cast<volatile unsigned int*>(h->h_oflow + 1) = 0u;  // reported once
+      return fail(h, TIC_ERR_INVALID, es == 1 ? "entropy stage: symbol outside the table or of zero probability"
+                                                : "entropy stage: output slot too small (use tic_entropy_bound)");
+    }
+  }
+  return TIC_OK;
+}
+
 int pow2ceil(int v) {
   int p = 1;
   while (p < v) p <<= 1;
@@ -118,22 +150,16 @@ void same_pad(int in, int s, int* out, int* before) {
 template <int OCB, int S>
 int launch_conv_t(tic_codec* h, const LayerArgs& a, const SmemPlan& sp, dim3 grid, size_t smem) {
   auto k = conv3x3_simt_kernel<OCB, S>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    TIC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemAttrCache cache;
+  TIC_CUDA(h, cache.ensure(reinterpret_cast<const void*>(k), smem, 48 * 1024));
   k<<<grid, kThreads, smem, h->stream>>>(a, sp);
   return TIC_OK;
 }
 template <int OCB>
 int launch_deconv_t(tic_codec* h, const LayerArgs& a, const SmemPlan& sp, dim3 grid, size_t smem) {
   auto k = deconv3x3_simt_kernel<OCB>;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    TIC_CUDA(h, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static SmemAttrCache cache;
+  TIC_CUDA(h, cache.ensure(reinterpret_cast<const void*>(k), smem, 48 * 1024));
   k<<<grid, kThreads, smem, h->stream>>>(a, sp);
   return TIC_OK;
 }
@@ -271,15 +297,12 @@ struct LayerGroup {
 };
 
 long long l2_budget_bytes_per_group() {
-  static const long long mb = [] {
-    // 0 (default) disables grouping.  Measured on B200 (model_0, 12288 patches): 56 MB -> 20.3 ms per encode+decode
-    // step against 14.0 ms ungrouped: each extra (20 us) launch costs ~8 us of prologue (weight tiles, TMEM,
-    // cluster sync) and tail.  The schedule pays off only once a group runs as one persistent kernel.
-    const char* e = getenv("TIC_L2_BUDGET_MB");
-    const long long v = e ? atoll(e) : 0;
-    return v < 0 ? 0 : std::min<long long>(v, 4096);
-  }();
-  return mb << 20;
+  // 0 (default, and the only value outside -DTIC_ABLATE builds) disables grouping.  Measured on B200 (model_0, 12288
+  // patches): 56 MB -> 20.3 ms per encode+decode step against 14.0 ms ungrouped: each extra (20 us) launch costs ~8 us
+  // of prologue (weight tiles, TMEM, cluster sync) and tail.  The schedule pays off only once a group runs as one
+  // persistent kernel.
+  const long long v = tic_env_int("TIC_L2_BUDGET_MB", 0);
+  return (v < 0 ? 0 : std::min<long long>(v, 4096)) << 20;
 }
 
 std::vector<LayerGroup> plan_groups(const Graph& g, const std::vector<LayerShape>& sh, int L, int n, bool enable) {
@@ -418,10 +441,11 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
         const int blocks = (int)std::min<long long>((count + 255) / 256, (long long)h->num_sms * 8);
         if (io_in.mode == IO_ACT)
           u16_split_f32_kernel<<<blocks, 256, 0, h->stream>>>(reinterpret_cast<const float*>(io_in.in) + (long long)s0 * per, hi,
-                                                             hi + count, count);
+                                                             hi + count, count, h->d_oflow);
         else
           u16_split_symlut_kernel<<<blocks, 256, 0, h->stream>>>(
-              reinterpret_cast<const uint8_t*>(io_in.in) + ((long long)io_in.geo.n0 + s0) * per, h->d_symlut, hi, hi + count, count);
+              reinterpret_cast<const uint8_t*>(io_in.in) + ((long long)io_in.geo.n0 + s0) * per, h->d_symlut, hi, hi + count, count,
+              h->d_oflow);
         h->launches++;
         TIC_CUDA(h, cudaGetLastError());
         cur = 0;
@@ -445,13 +469,8 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
         a.bias = ly.b;
         a.q = h->q;
         a.hist = h->d_hist;
-        {
-          static const int dbg = [] {
-            const char* e = getenv("TIC_DBG");
-            return e ? atoi(e) : 0;
-          }();
-          a.dbg = dbg;
-        }
+        a.oflow = h->d_oflow;
+        a.dbg = tic_env_int("TIC_DBG", 0);  // -DTIC_ABLATE builds only
         for (int c = 0; c < 3; ++c) {
           a.mean[c] = g.mean[c];
           a.stdv[c] = g.stdv[c];
@@ -566,12 +585,8 @@ int patches_per_chunk(const tic_codec* h, int P) {
 // at both ends.
 // TIC_HOST_RAMP=1 selects the ramp, TIC_HOST_CHUNKS the equal-chunk count.
 std::vector<int64_t> host_chunk_schedule(int64_t units, int64_t cap, double patches128_per_unit) {
-  static const bool ramp = getenv("TIC_HOST_RAMP") != nullptr;
-  static const int want = [] {
-    const char* e = getenv("TIC_HOST_CHUNKS");
-    const int v = e ? atoi(e) : 16;
-    return v < 1 ? 1 : v;
-  }();
+  const bool ramp = tic_env_set("TIC_HOST_RAMP");                      // -DTIC_ABLATE builds only
+  const int want = std::max(1, tic_env_int("TIC_HOST_CHUNKS", 16));   // -DTIC_ABLATE builds only
   cap = std::max<int64_t>(1, std::min(cap, units));
   std::vector<int64_t> out;
   if (!ramp) {
@@ -611,6 +626,7 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
           size_t out_unit_bytes, bool inout_same, RunFn run, double patches128_per_unit = 1.0) {
   if (units <= 0) return TIC_OK;
   TIC_CUDA(h, cudaSetDevice(h->device));
+  if (int st = overflow_status(h)) return st;
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
   if (mem == TIC_MEM_DEVICE) {
     upc *= 4;  // no staging to overlap with: fewer, longer launch sequences (up to 16384 patches of 128x128 each)
@@ -645,6 +661,9 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
     for (int b = 0; b < 2; ++b) TIC_CUDA(h, cudaMalloc(&h->stage_out[b], out_need));
     h->stage_out_bytes = out_need;
   }
+  // the pipeline proper runs inside a lambda: ANY failure (a CUDA call, a layer launch) drains the three streams before
+  // the error is returned, so no copy is still in flight into or out of the caller's buffers
+  const int rc_pipe = [&]() -> int {
   int64_t u0 = 0;
   for (int64_t idx = 0; idx < (int64_t)sched.size(); u0 += sched[idx], ++idx) {
     const int b = (int)(idx & 1);
@@ -671,6 +690,12 @@ int drive(tic_codec* h, int mem, const void* in, void* out, int64_t units, int64
   TIC_CUDA(h, cudaStreamSynchronize(h->s_d2h));
   TIC_CUDA(h, cudaStreamSynchronize(h->stream));
   return TIC_OK;
+  }();
+  if (rc_pipe != TIC_OK) {
+    quiesce(h);
+    return rc_pipe;
+  }
+  return overflow_status(h);
 }
 
 Geo patch_geo(int P, long long n0) {
@@ -756,6 +781,12 @@ int tic_create(tic_codec** out, int device) {
   cudaMemset(h->d_hist, 0, 256 * sizeof(unsigned long long));
   if ((e = cudaMalloc(&h->d_symlut, 256 * sizeof(float))) != cudaSuccess) return bail("cudaMalloc", e);
   cudaMemset(h->d_symlut, 0, 256 * sizeof(float));
+  if ((e = cudaHostAlloc((void**)&h->h_oflow, 2 * sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable)) != cudaSuccess)
+    return bail("cudaHostAlloc", e);
+  h->h_oflow[0] = h->h_oflow[1] = 0u;
+  if ((e = cudaMalloc(&h->d_cum, (kEntropyMaxSymbols + 1) * sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc", e);
+  if ((e = cudaHostGetDevicePointer((void**)&h->d_oflow, h->h_oflow, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
+  cudaEventCreateWithFlags(&h->ev_switch, cudaEventDisableTiming);
   *out = h;
   return TIC_OK;
 }
@@ -792,6 +823,9 @@ void tic_destroy(tic_codec* h) {
   cudaEventDestroy(h->ev_t1);
   if (h->d_hist) cudaFree(h->d_hist);
   if (h->d_symlut) cudaFree(h->d_symlut);
+  if (h->h_oflow) cudaFreeHost(h->h_oflow);
+  if (h->d_cum) cudaFree(h->d_cum);
+  if (h->ev_switch) cudaEventDestroy(h->ev_switch);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
   if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
@@ -802,11 +836,21 @@ const char* tic_last_error(const tic_codec* h) { return h ? h->err.c_str() : "nu
 
 int tic_set_stream(tic_codec* h, void* cuda_stream) {
   if (!h) return TIC_ERR_INVALID;
+  cudaStream_t next = (cudaStream_t)cuda_stream;
+  if (next == h->stream) return TIC_OK;
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  // The handle's workspaces (rotating activation buffers, weight images under construction, the histogram, the
+  // staging sets) are shared by everything it launches: work queued on the old stream must finish before work on the
+  // new stream may touch them.  Device-side ordering (event), no host stall — except when leaving the private
+  // stream, which is destroyed.
   if (h->own_stream && h->stream) {
     cudaStreamSynchronize(h->stream);
     cudaStreamDestroy(h->stream);
+  } else {
+    TIC_CUDA(h, cudaEventRecord(h->ev_switch, h->stream));
+    TIC_CUDA(h, cudaStreamWaitEvent(next, h->ev_switch, 0));
   }
-  h->stream = (cudaStream_t)cuda_stream;
+  h->stream = next;
   h->own_stream = false;
   return TIC_OK;
 }
@@ -815,6 +859,11 @@ int tic_set_compute_mode(tic_codec* h, int mode) {
   if (!h) return TIC_ERR_INVALID;
   if (mode < TIC_COMPUTE_FP32 || mode > TIC_COMPUTE_TENSOR_F16X3) return fail(h, TIC_ERR_INVALID, "unknown compute mode %d", mode);
   h->mode = mode;
+  if (h->h_oflow) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    *h->h_oflow = 0u;  // the fp16-range flag belongs to the previous mode's runs
+  }
   return TIC_OK;
 }
 
@@ -1119,6 +1168,8 @@ int tic_roundtrip_images(tic_codec* h, const uint8_t* images, int64_t n_images, 
   if ((rc = grow(h->stage_out, &h->stage_out_bytes, (size_t)ipc * rec_unit)) != TIC_OK) return rc;
   // Three streams, two staging sets: H2D of chunk i+1 (one PCIe direction) runs under the kernels of chunk i and
   // the D2H of chunk i-1 (the other direction).
+  if (int st = overflow_status(h)) return st;
+  const int rc_pipe = [&]() -> int {  // any failure drains the three streams before returning (see drive())
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
   int64_t u0 = 0;
   for (int64_t idx = 0; idx < (int64_t)sched.size(); u0 += sched[idx], ++idx) {
@@ -1164,6 +1215,12 @@ int tic_roundtrip_images(tic_codec* h, const uint8_t* images, int64_t n_images, 
   TIC_CUDA(h, cudaStreamSynchronize(h->s_d2h));
   TIC_CUDA(h, cudaStreamSynchronize(h->stream));
   return TIC_OK;
+  }();
+  if (rc_pipe != TIC_OK) {
+    quiesce(h);
+    return rc_pipe;
+  }
+  return overflow_status(h);
 }
 
 int tic_postfilter_patches(tic_codec* h, const float* tiles, int64_t n, int P, float* out, int mem) {
@@ -1331,6 +1388,38 @@ int tic_position_sums(tic_codec* h, const uint8_t* symbols, int64_t n, int64_t n
   return TIC_OK;
 }
 
+int tic_position_sums_batched(tic_codec* h, const uint8_t* symbols, int64_t n, int64_t npos, int64_t batch, uint64_t* sums,
+                              int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n < 0 || npos <= 0 || batch <= 0 || !sums || (n > 0 && !symbols)) return fail(h, TIC_ERR_INVALID, "bad arguments");
+  const int64_t nb = (n + batch - 1) / batch;
+  if (nb == 0) return TIC_OK;
+  if (nb > 65535) return fail(h, TIC_ERR_INVALID, "too many batches (%lld)", (long long)nb);
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  const uint8_t* dsym = symbols;
+  unsigned long long* dsum = (unsigned long long*)sums;
+  void *tmp_sym = nullptr, *tmp_sum = nullptr;
+  if (mem == TIC_MEM_HOST) {
+    TIC_CUDA(h, cudaMalloc(&tmp_sym, (size_t)(n * npos)));
+    TIC_CUDA(h, cudaMalloc(&tmp_sum, (size_t)(nb * npos) * 8));
+    TIC_CUDA(h, cudaMemcpyAsync(tmp_sym, symbols, (size_t)(n * npos), cudaMemcpyHostToDevice, h->stream));
+    dsym = (const uint8_t*)tmp_sym;
+    dsum = (unsigned long long*)tmp_sum;
+  }
+  position_sums_batched_kernel<<<dim3((unsigned)((npos + 255) / 256), (unsigned)nb), 256, 0, h->stream>>>(dsym, n, npos, batch, dsum);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && mem == TIC_MEM_HOST)
+    e = cudaMemcpyAsync(sums, tmp_sum, (size_t)(nb * npos) * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (mem == TIC_MEM_HOST) {
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp_sym);
+    cudaFree(tmp_sum);
+  }
+  if (e != cudaSuccess) return fail(h, TIC_ERR_CUDA, "position sums failed: %s", cudaGetErrorString(e));
+  return TIC_OK;
+}
+
 static int prof_collect(tic_codec* h) {
   for (auto& r : h->prof_pending) {
     float ms = 0.f;
@@ -1376,6 +1465,124 @@ int tic_profile_read(tic_codec* h, int graph, float* ms, int64_t* launches, int 
     launches[i] = i < (int)h->prof_n[graph].size() ? h->prof_n[graph][i] : 0;
   }
   return TIC_OK;
+}
+
+// ---- GPU entropy stage ------------------------------------------------------------------------
+int64_t tic_entropy_bound(int64_t stream_len) { return (tic_rc_bound(stream_len < 0 ? 0 : stream_len) + 15) & ~(int64_t)15; }
+
+static int entropy_table(tic_codec* h, const uint32_t* cum, int n_cum) {
+  if (!cum || n_cum < 2 || n_cum - 1 > kEntropyMaxSymbols) return fail(h, TIC_ERR_INVALID, "entropy stage: tables of 1..256 symbols");
+  if (cum[0] != 0) return fail(h, TIC_ERR_INVALID, "entropy stage: cumulative frequencies must start at 0");
+  for (int i = 1; i < n_cum; ++i)
+    if (cum[i] < cum[i - 1]) return fail(h, TIC_ERR_INVALID, "entropy stage: cumulative frequencies must not decrease");
+  if (cum[n_cum - 1] == 0 || cum[n_cum - 1] > TIC_RC_MAX_TOTAL) return fail(h, TIC_ERR_INVALID, "entropy stage: frequency total must be in [1, 65536]");
+  TIC_CUDA(h, cudaMemcpyAsync(h->d_cum, cum, (size_t)n_cum * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+  return TIC_OK;
+}
+
+int tic_entropy_encode(tic_codec* h, const uint8_t* symbols, int64_t n_streams, int64_t stream_len, const uint32_t* cum_freq,
+                       int n_cum, uint8_t* out, int64_t out_stride, int64_t* out_bytes, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n_streams < 0 || stream_len < 0 || out_stride < 0 || (n_streams > 0 && (!symbols || !out || !out_bytes)))
+    return fail(h, TIC_ERR_INVALID, "bad arguments");
+  if (n_streams == 0) return TIC_OK;
+  if (n_streams > 0x7fffffffLL) return fail(h, TIC_ERR_INVALID, "too many streams");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  if (int st = overflow_status(h)) return st;
+  int rc = entropy_table(h, cum_freq, n_cum);
+  if (rc != TIC_OK) return rc;
+  const uint8_t* dsym = symbols;
+  uint8_t* dout = out;
+  long long* dbytes = reinterpret_cast<long long*>(out_bytes);
+  void *t_sym = nullptr, *t_out = nullptr, *t_bytes = nullptr;
+  if (mem == TIC_MEM_HOST) {
+    TIC_CUDA(h, cudaMalloc(&t_sym, (size_t)std::max<int64_t>(16, n_streams * stream_len)));
+    TIC_CUDA(h, cudaMalloc(&t_out, (size_t)std::max<int64_t>(16, n_streams * out_stride)));
+    TIC_CUDA(h, cudaMalloc(&t_bytes, (size_t)n_streams * 8));
+    TIC_CUDA(h, cudaMemcpyAsync(t_sym, symbols, (size_t)(n_streams * stream_len), cudaMemcpyHostToDevice, h->stream));
+    dsym = (const uint8_t*)t_sym;
+    dout = (uint8_t*)t_out;
+    dbytes = (long long*)t_bytes;
+  }
+  TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
+  rc_encode_kernel<<<(unsigned)n_streams, 32, 0, h->stream>>>(dsym, stream_len, h->d_cum, n_cum, dout, out_stride, dbytes, h->d_oflow + 1);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  cudaEventRecord(h->ev_t1, h->stream);
+  if (mem == TIC_MEM_HOST) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_bytes, t_bytes, (size_t)n_streams * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    // only the stored bytes of every stream come back
+    for (int64_t i = 0; e == cudaSuccess && i < n_streams; ++i)
+      if (out_bytes[i] > 0)
+        e = cudaMemcpyAsync(out + i * out_stride, (uint8_t*)t_out + i * out_stride, (size_t)out_bytes[i], cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(t_sym);
+    cudaFree(t_out);
+    cudaFree(t_bytes);
+    if (e != cudaSuccess) return fail(h, TIC_ERR_CUDA, "entropy encode failed: %s", cudaGetErrorString(e));
+    return overflow_status(h);
+  }
+  if (e != cudaSuccess) return fail(h, TIC_ERR_CUDA, "entropy encode launch failed: %s", cudaGetErrorString(e));
+  return TIC_OK;
+}
+
+int tic_entropy_decode(tic_codec* h, const uint8_t* in, int64_t n_streams, int64_t in_stride, const int64_t* in_bytes,
+                       const uint32_t* cum_freq, int n_cum, uint8_t* symbols, int64_t stream_len, int mem) {
+  if (!h) return TIC_ERR_INVALID;
+  if (n_streams < 0 || stream_len < 0 || in_stride < 0 || (n_streams > 0 && (!symbols || !in || !in_bytes)))
+    return fail(h, TIC_ERR_INVALID, "bad arguments");
+  if (n_streams == 0) return TIC_OK;
+  if (n_streams > 0x7fffffffLL) return fail(h, TIC_ERR_INVALID, "too many streams");
+  if (in_stride % 16 != 0) return fail(h, TIC_ERR_INVALID, "entropy decode: in_stride must be a multiple of 16 bytes");
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  if (int st = overflow_status(h)) return st;
+  int rc = entropy_table(h, cum_freq, n_cum);
+  if (rc != TIC_OK) return rc;
+  const uint8_t* din = in;
+  const long long* dbytes = reinterpret_cast<const long long*>(in_bytes);
+  uint8_t* dsym = symbols;
+  void *t_in = nullptr, *t_bytes = nullptr, *t_sym = nullptr;
+  if (mem == TIC_MEM_HOST) {
+    for (int64_t i = 0; i < n_streams; ++i)
+      if (in_bytes[i] < 0 || in_bytes[i] > in_stride)
+        return fail(h, TIC_ERR_INVALID, "entropy decode: stream %lld has %lld bytes in a %lld-byte slot", (long long)i,
+                    (long long)in_bytes[i], (long long)in_stride);
+    TIC_CUDA(h, cudaMalloc(&t_in, (size_t)std::max<int64_t>(16, n_streams * in_stride)));
+    TIC_CUDA(h, cudaMalloc(&t_bytes, (size_t)n_streams * 8));
+    TIC_CUDA(h, cudaMalloc(&t_sym, (size_t)std::max<int64_t>(16, n_streams * stream_len)));
+    for (int64_t i = 0; i < n_streams; ++i) {
+      if (in_bytes[i] > 0)
+        TIC_CUDA(h, cudaMemcpyAsync((uint8_t*)t_in + i * in_stride, in + i * in_stride, (size_t)in_bytes[i], cudaMemcpyHostToDevice, h->stream));
+    }
+    TIC_CUDA(h, cudaMemcpyAsync(t_bytes, in_bytes, (size_t)n_streams * 8, cudaMemcpyHostToDevice, h->stream));
+    din = (const uint8_t*)t_in;
+    dbytes = (const long long*)t_bytes;
+    dsym = (uint8_t*)t_sym;
+  } else if ((reinterpret_cast<uintptr_t>(in) & 15) != 0) {
+    return fail(h, TIC_ERR_INVALID, "entropy decode: the stream buffer must be 16-byte aligned");
+  }
+  TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
+  rc_decode_kernel<<<(unsigned)n_streams, 32, 0, h->stream>>>(din, in_stride, dbytes, h->d_cum, n_cum, dsym, stream_len);
+  h->launches++;
+  cudaError_t e = cudaGetLastError();
+  cudaEventRecord(h->ev_t1, h->stream);
+  if (mem == TIC_MEM_HOST) {
+    if (e == cudaSuccess) e = cudaMemcpyAsync(symbols, t_sym, (size_t)(n_streams * stream_len), cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(t_in);
+    cudaFree(t_bytes);
+    cudaFree(t_sym);
+  }
+  if (e != cudaSuccess) return fail(h, TIC_ERR_CUDA, "entropy decode failed: %s", cudaGetErrorString(e));
+  return TIC_OK;
+}
+
+int tic_check_status(tic_codec* h) {
+  if (!h) return TIC_ERR_INVALID;
+  TIC_CUDA(h, cudaSetDevice(h->device));
+  TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+  return overflow_status(h);
 }
 
 uint32_t tic_crc32c(const void* data, uint64_t n) {

@@ -4,9 +4,47 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <mutex>
 #include "../../include/tic_math.h"
 
 namespace tic {
+
+// Measurement aids (stage ablations, alternative schedules) exist only in builds made with -DTIC_ABLATE
+// (tools/build_ablate.sh).  The shipped library ignores every TIC_* environment variable: a stray variable must
+// never change what a kernel computes.
+#ifdef TIC_ABLATE
+inline int tic_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+inline bool tic_env_set(const char* name) { return getenv(name) != nullptr; }
+#define TIC_DBG_BITS(x) (x)
+#else
+inline int tic_env_int(const char*, int dflt) { return dflt; }
+inline bool tic_env_set(const char*) { return false; }
+#define TIC_DBG_BITS(x) 0
+#endif
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: the "already configured" cache of a
+// launcher is keyed by the current device (one handle per device, several devices per process), and guarded by a mutex
+// because handles of different devices may launch from different threads.
+struct SmemAttrCache {
+  static constexpr int kMaxDevices = 64;
+  size_t have[kMaxDevices] = {};
+  std::mutex mu;
+  cudaError_t ensure(const void* kernel, size_t smem, size_t always_above = 0) {
+    if (smem <= always_above) return cudaSuccess;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < kMaxDevices && smem <= have[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && dev >= 0 && dev < kMaxDevices) have[dev] = smem;
+    return e;
+  }
+};
 
 // How the first layer reads its input / the last layer writes its output.
 enum IoMode : int {
@@ -123,7 +161,8 @@ struct LayerArgs {
   // IO_ACT16 tensors: `in` / `out` / `res` point at the hi plane, the lo' plane starts *_lo_off halves later
   long long in_lo_off, out_lo_off, res_lo_off;
   int res16;             // residual source is a pair-plane tensor
-  int dbg;               // measurement aid (env TIC_DBG bit 8: the staged epilogue skips its global stores)
+  unsigned int* oflow;   // sticky fp16-range flag (host-mapped): set to 1 when a pair-plane split sees |x| >= 65504
+  int dbg;               // -DTIC_ABLATE builds only (env TIC_DBG bit 8: the staged epilogue skips its global stores)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) { return act ? fmaxf(v, 0.0f) : v; }
@@ -136,6 +175,19 @@ __device__ __forceinline__ void split16(float v, __half& hi, __half& lo) {
 }
 __device__ __forceinline__ float join16(__half hi, __half lo) {
   return __fmaf_rn(__half2float(lo), 1.0f / 2048.0f, __half2float(hi));
+}
+
+// fp16-range guard of the pair-plane format (include/tic.h: TIC_COMPUTE_TENSOR_F16X3 needs |activation| < 65504).
+// A split of a larger value gives hi = inf; every epilogue keeps a running max of |hi| (one HMNMX2 per two
+// elements) and raises the handle's sticky flag once per warp at the end of its tile loop.
+__device__ __forceinline__ void ovf_track(__half2& m, const __half2 h) { m = __hmax2(m, __habs2(h)); }
+__device__ __forceinline__ bool ovf_hit(const __half2 m) {
+  const uint32_t w = *reinterpret_cast<const uint32_t*>(&m);
+  return (w & 0x7fffu) >= 0x7c00u || ((w >> 16) & 0x7fffu) >= 0x7c00u;
+}
+__device__ __forceinline__ bool ovf_hit1(const __half h) { return (__half_as_ushort(h) & 0x7fffu) >= 0x7c00u; }
+__device__ __forceinline__ void ovf_raise(unsigned int* flag) {
+  if (flag) *reinterpret_cast<volatile unsigned int*>(flag) = 1u;
 }
 
 }  // namespace tic

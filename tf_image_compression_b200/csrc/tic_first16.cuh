@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
     const int grp = m >> 3, xx = m & 7;
     const int hh = grp / p.bn, nb = grp % p.bn;
     int h_ones = 0, h_valid = 0;
+    __half2 omax = __floats2half2_rn(0.f, 0.f);
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if (staged && (int)(it & 1u) != half) continue;  // staged: a warp group owns every other tile
@@ -246,15 +247,16 @@ __global__ void __launch_bounds__(kF16Threads, 1) f16_first_kernel(const F16Para
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
       if (staged) {
         u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * p.bh + hh, (int)tx * 8 + xx, n < p.n, s_bias,
-                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0, &bars->acc_empty[b], 1);
+                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0, &bars->acc_empty[b], 1, omax);
         continue;  // the staged epilogue released the buffer itself
       } else
         u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * p.bh + hh, (int)tx * 8 + xx, n < p.n, half, s_bias, s_hist, h_ones,
-                                  h_valid);
+                                  h_valid, omax);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
     }
+    if (ovf_hit(omax)) ovf_raise(a.oflow);
     if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
       if (a.q == 2) {
         h_ones = __reduce_add_sync(0xffffffffu, h_ones);
@@ -525,7 +527,7 @@ f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params 
     if ((long long)blockIdx.x < p.num_tiles) request(blockIdx.x, raw, okm);
     if ((long long)blockIdx.x + gridDim.x < p.num_tiles) request(blockIdx.x + gridDim.x, raw_b, okm_b);
     uint32_t it = 0;
-    if (p.dbg & 2) {
+    if (TIC_DBG_BITS(p.dbg) & 2) {
       for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int s = it % kW2Stages;
         ptx::mbar_wait(&bars->empty[s], ((it / kW2Stages) & 1) ^ 1);
@@ -599,7 +601,7 @@ f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params 
       ptx::mbar_wait(&bars->acc_empty[b], ((it >> nbshift) & 1) ^ 1);
       ptx::mbar_wait(&bars->full[s], (it / kW2Stages) & 1);
       ptx::tc_fence_after();
-      if (!(p.dbg & 1) && ptx::elect_one()) {
+      if (!(TIC_DBG_BITS(p.dbg) & 1) && ptx::elect_one()) {
         const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * 10240) >> 4) | a_lbo;
         const uint32_t al = ah + (kW2Plane >> 4);
         const uint32_t d = tmem_base + b * pairw;
@@ -624,6 +626,7 @@ f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params 
     const int m = q4 * 32 + lane;
     const int hh = m >> 3, xx = m & 7;
     int h_ones = 0, h_valid = 0;
+    __half2 omax = __floats2half2_rn(0.f, 0.f);
     uint32_t it = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if (staged && (int)(it & 1u) != half) continue;  // staged: a warp group owns every other tile
@@ -635,17 +638,18 @@ f16_first_s2_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params 
       fast_divmod(tq, p.ty_d, tn, ty);
       const int n = (int)tn;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * pairw;
-      if (p.dbg & 4) {
+      if (TIC_DBG_BITS(p.dbg) & 4) {
       } else if (staged) {
         u16_epilogue_tile_staged<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, s_bias,
-                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0, &bars->acc_empty[b], 1);
+                                         s_stage + (size_t)(warp - 8) * kU16StagePerWarp, lane, 0, &bars->acc_empty[b], 1, omax);
         continue;  // the staged epilogue released the buffer itself
       } else
-        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid);
+        u16_epilogue_tile<U16_S1>(a, NPAD, 0, 1, tbuf, n, (int)ty * 16 + hh, (int)tx * 8 + xx, true, half, s_bias, s_hist, h_ones, h_valid, omax);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
     }
+    if (ovf_hit(omax)) ovf_raise(a.oflow);
     if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
       if (a.q == 2) {
         h_ones = __reduce_add_sync(0xffffffffu, h_ones);
@@ -691,7 +695,7 @@ constexpr int kT2Stages = 6;                       // operand stages = raw-windo
 template <int CEND>
 __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const uint32_t tbuf, const int NPAD, const int n, const int yt,
                                                      const int xt, const float* s_bias, const uint32_t stage, const int lane,
-                                                     uint64_t* rel_bar) {
+                                                     uint64_t* rel_bar, __half2& omax) {
   constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane
   constexpr int MSH = M == 2 ? 1 : 2;
   constexpr int FSH = 3 - MSH;                       // swizzle: chunk ^= (pixel >> FSH) & (M - 1)
@@ -723,7 +727,7 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const u
     }
     uint32_t hp[8], lp[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
+    for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i], omax);
     sts128(sp + (uint32_t)(((2 * ci) ^ sw) << 4), hp[0], hp[1], hp[2], hp[3]);
     sts128(sp + (uint32_t)(((2 * ci + 1) ^ sw) << 4), hp[4], hp[5], hp[6], hp[7]);
     sts128(sp + kT2LoOff + (uint32_t)(((2 * ci) ^ sw) << 4), lp[0], lp[1], lp[2], lp[3]);
@@ -741,7 +745,7 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const u
     const int swq = (px >> FSH) & (M - 1);
     const uint32_t src = stage + (uint32_t)((px * M + (cq ^ swq)) << 4);
     const uint4 vh = lds128(src), vl = lds128(src + kT2LoOff);
-    if (!(a.dbg & 8)) {
+    if (!(TIC_DBG_BITS(a.dbg) & 8)) {
       ohi[(long long)base + cq] = vh;
       olo[(long long)base + cq] = vl;
     }
@@ -821,7 +825,7 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     const uint8_t* rawb = s_rawwin + (size_t)slot * RAW_STAGE;
     uint8_t* stb = s_a + (size_t)slot * 10240;
     uint32_t ph = 0;
-    if (p.dbg & 2) {  // measurement aid: consume the raw windows, publish empty stages
+    if (TIC_DBG_BITS(p.dbg) & 2) {  // measurement aid: consume the raw windows, publish empty stages
       for (long long tile = blockIdx.x + (long long)warp * gridDim.x; tile < p.num_tiles; tile += 6LL * gridDim.x, ph ^= 1u) {
         ptx::mbar_wait(&bars->raw_full[slot], ph);
         ptx::mbar_wait(&bars->empty[slot], ph ^ 1u);
@@ -930,7 +934,7 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
       ptx::mbar_wait(&bars->acc_empty[b], ((it >> 2) & 1) ^ 1);
       ptx::mbar_wait(&bars->full[s], sph);
       ptx::tc_fence_after();
-      if (!(p.dbg & 1) && ptx::elect_one()) {
+      if (!(TIC_DBG_BITS(p.dbg) & 1) && ptx::elect_one()) {
         const uint32_t ah = (ptx::smem_u32(s_a + (size_t)s * 10240) >> 4) | a_lbo;
         const uint32_t al = ah + (kW2Plane >> 4);
         const uint32_t d = tmem_base + b * pairw;
@@ -961,21 +965,23 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     const uint32_t stage = ptx::smem_u32(s_stage + (size_t)ew * kT2StagePerWarp);
     const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)group * pairw;
     uint32_t use = 0;
+    __half2 omax = __floats2half2_rn(0.f, 0.f);
     for (long long tile = blockIdx.x + (long long)group * gridDim.x; tile < p.num_tiles; tile += 4LL * gridDim.x, ++use) {
       ptx::mbar_wait(&bars->acc_full[group], use & 1);
       ptx::tc_fence_after();
       uint32_t tq, tx, ty, tn;
       fast_divmod((uint32_t)tile, p.tx_d, tq, tx);
       fast_divmod(tq, p.ty_d, tn, ty);
-      if (p.dbg & 4) {
+      if (TIC_DBG_BITS(p.dbg) & 4) {
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[group]);
       } else if (NPAD == 32)
-        f16_t2_epilogue_tile<32>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group]);
+        f16_t2_epilogue_tile<32>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group], omax);
       else
-        f16_t2_epilogue_tile<16>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group]);
+        f16_t2_epilogue_tile<16>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group], omax);
     }
+    if (ovf_hit(omax)) ovf_raise(a.oflow);
   }
 
   ptx::tc_fence_before();
@@ -1040,13 +1046,7 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   p.ty_d = make_fastdiv((uint32_t)p.tiles_y);
   p.txy_d = make_fastdiv((uint32_t)(p.tiles_x * p.tiles_y));
   p.npad = a.cout;
-  {
-    static const int dbg = [] {
-      const char* e = getenv("TIC_DBG");
-      return e ? atoi(e) : 0;
-    }();
-    p.dbg = dbg;
-  }
+  p.dbg = tic_env_int("TIC_DBG", 0);  // -DTIC_ABLATE builds only
   p.nbuf = std::min(4, 512 / (2 * p.npad));
   const bool windowed = stride == 2 && p.bn == 1;  // operands straight from the staged input tile (no im2col)
   if (!fw->img || fw->windowed != windowed) {
@@ -1066,7 +1066,7 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
   CUtensorMap tm_img{};
   p.use_tma = 0;
   if (windowed && f16_first_tma_ok(a)) {
-    static const bool off = getenv("TIC_FIRST_NO_TMA") != nullptr;
+    const bool off = tic_env_set("TIC_FIRST_NO_TMA");  // -DTIC_ABLATE builds only
     auto encode = umma_encode_fn();
     if (!off && encode) {
       const Geo& g = a.geo;
@@ -1086,19 +1086,13 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
     }
   }
   const int grid = (int)std::min<long long>(p.num_tiles, num_sms);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(f16_first_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(f16_first_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(f16_first_s2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w2) != cudaSuccess)
-      return fail("cudaFuncSetAttribute(first-layer kernel) failed", -2);
-    configured = true;
-  }
+  static SmemAttrCache cache_k1, cache_k2, cache_w2;
+  if (cache_k1.ensure(reinterpret_cast<const void*>(f16_first_kernel<1>), smem) != cudaSuccess ||
+      cache_k2.ensure(reinterpret_cast<const void*>(f16_first_kernel<2>), smem) != cudaSuccess ||
+      cache_w2.ensure(reinterpret_cast<const void*>(f16_first_s2_kernel), smem_w2) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(first-layer kernel) failed", -2);
   // the TMA-fed, pair-plane-output kernel (16 epilogue warps) when the launch qualifies; TIC_FIRST_T2=0 keeps the general one
-  static const bool t2_off = [] {
-    const char* e = getenv("TIC_FIRST_T2");
-    return e && e[0] == '0';
-  }();
+  const bool t2_off = tic_env_int("TIC_FIRST_T2", 1) == 0;  // -DTIC_ABLATE builds only
   const bool t2 = windowed && p.use_tma && !t2_off && a.out_mode == IO_ACT16 && (a.cout == 32 || a.cout == 16) &&
                   p.nbuf == 4;
   // the general kernel's TMA builders take u8 windows of an un-shifted grid only
@@ -1107,15 +1101,12 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
     const bool f32in = a.in_mode == IO_F32_NORM;
     const size_t smem_t2 = kT2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp +
                            kT2Stages * (f32in ? kRawStageF32 : kRawStage) + sizeof(W2SmemBars) + 1024;
-    static bool t2_configured = false;
-    if (!t2_configured) {
-      const int big = (int)(kT2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kT2Stages * kRawStageF32 +
-                            sizeof(W2SmemBars) + 1024);
-      if (cudaFuncSetAttribute(f16_first_s2_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess ||
-          cudaFuncSetAttribute(f16_first_s2_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big) != cudaSuccess)
-        return fail("cudaFuncSetAttribute(first-layer TMA kernel) failed", -2);
-      t2_configured = true;
-    }
+    static SmemAttrCache cache_t2u, cache_t2f;
+    const size_t big = kT2Stages * 10240 + 192 * 64 + kT2EpiWarps * kT2StagePerWarp + kT2Stages * kRawStageF32 +
+                       sizeof(W2SmemBars) + 1024;
+    if (cache_t2u.ensure(reinterpret_cast<const void*>(f16_first_s2_tma_kernel<false>), big) != cudaSuccess ||
+        cache_t2f.ensure(reinterpret_cast<const void*>(f16_first_s2_tma_kernel<true>), big) != cudaSuccess)
+      return fail("cudaFuncSetAttribute(first-layer TMA kernel) failed", -2);
     if (f32in)
       f16_first_s2_tma_kernel<true><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
     else

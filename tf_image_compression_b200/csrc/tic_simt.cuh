@@ -214,6 +214,7 @@ __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, in
             __half* l4 = reinterpret_cast<__half*>(&ql);
 #pragma unroll
             for (int e = 0; e < 4; ++e) split16(v[i + e], h4[e], l4[e]);
+            if (ovf_hit1(h4[0]) | ovf_hit1(h4[1]) | ovf_hit1(h4[2]) | ovf_hit1(h4[3])) ovf_raise(a.oflow);
             *reinterpret_cast<uint2*>(oh + i) = qh;
             *reinterpret_cast<uint2*>(ol + i) = ql;
           }
@@ -221,7 +222,10 @@ __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, in
       } else {
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-          if (oc + i < a.cout) split16(v[i], oh[i], ol[i]);
+          if (oc + i < a.cout) {
+            split16(v[i], oh[i], ol[i]);
+            if (ovf_hit1(oh[i])) ovf_raise(a.oflow);
+          }
       }
       break;
     }
@@ -528,6 +532,18 @@ __global__ void position_sums_kernel(const uint8_t* __restrict__ sym, long long 
   unsigned long long s = 0;
   for (long long i = 0; i < n; ++i) s += sym[i * npos + pos];
   sums[pos] += s;
+}
+
+// the same per batch of `batch` patches: sums[b][pos] = sum over the patches of batch b (the reference folds one
+// sess.run batch of 64 at a time into its running mean, cal_encoded_distribution.py:111-128); grid.y = batches
+__global__ void position_sums_batched_kernel(const uint8_t* __restrict__ sym, long long n, long long npos, long long batch,
+                                             unsigned long long* __restrict__ sums) {
+  const long long pos = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= npos) return;
+  const long long b = blockIdx.y, i0 = b * batch, i1 = min(n, i0 + batch);
+  unsigned long long s = 0;
+  for (long long i = i0; i < i1; ++i) s += sym[i * npos + pos];
+  sums[b * npos + pos] = s;
 }
 
 }  // namespace tic

@@ -495,11 +495,10 @@ template <int MODE, bool THREE_PASS>
 inline cudaError_t umma_launch_t(cudaStream_t stream, const CUtensorMap& tm, const UmmaParams& p, const LayerArgs& a, int grid,
                                  size_t smem) {
   auto k = umma_conv_kernel<MODE, THREE_PASS>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrCache cache;
+  {
+    cudaError_t e = cache.ensure(reinterpret_cast<const void*>(k), smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   k<<<grid, kUmmaThreads, smem, stream>>>(tm, p, a);
   return cudaGetLastError();

@@ -215,23 +215,30 @@ __global__ void u16_build_weights_pair_kernel(const float* __restrict__ w, int c
 }
 
 // fp32 NHWC -> fp16 pair planes (caller-provided f32 activations: tic_run_layers)
-__global__ void u16_split_f32_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long long count) {
+__global__ void u16_split_f32_kernel(const float* __restrict__ src, __half* __restrict__ hi, __half* __restrict__ lo, long long count,
+                                     unsigned int* oflow) {
+  bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     __half h, l;
     split16(src[i], h, l);
+    bad |= ovf_hit1(h);
     hi[i] = h;
     lo[i] = l;
   }
+  if (bad) ovf_raise(oflow);
 }
 // u8 symbols -> inverse-sigmoid LUT (model_0/model.py:153) -> fp16 pair planes
 __global__ void u16_split_symlut_kernel(const uint8_t* __restrict__ sym, const float* __restrict__ lut, __half* __restrict__ hi,
-                                        __half* __restrict__ lo, long long count) {
+                                        __half* __restrict__ lo, long long count, unsigned int* oflow) {
+  bool bad = false;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     __half h, l;
     split16(__ldg(lut + sym[i]), h, l);
+    bad |= ovf_hit1(h);
     hi[i] = h;
     lo[i] = l;
   }
+  if (bad) ovf_raise(oflow);
 }
 
 struct U16SmemBars {
@@ -286,6 +293,14 @@ __device__ __forceinline__ void u16_load_chunk(float (&v)[16], const uint32_t tb
 }
 
 // two values -> packed (hi, hi) and (lo', lo') half2 words; same arithmetic as split16
+__device__ __forceinline__ void split16x2(float v0, float v1, uint32_t& hp, uint32_t& lp, __half2& omax) {
+  const __half2 h = __floats2half2_rn(v0, v1);
+  ovf_track(omax, h);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(__fmul_rn(__fsub_rn(v0, hf.x), 2048.0f), __fmul_rn(__fsub_rn(v1, hf.y), 2048.0f));
+  hp = *reinterpret_cast<const uint32_t*>(&h);
+  lp = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split16x2(float v0, float v1, uint32_t& hp, uint32_t& lp) {
   const __half2 h = __floats2half2_rn(v0, v1);
   const float2 hf = __half22float2(h);
@@ -301,7 +316,7 @@ template <int MODE>
 __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
                                                   const uint32_t tbuf, const int n, const int yt, const int xt, const bool valid,
                                                   const int half, const float* s_bias, unsigned* s_hist, int& h_ones,
-                                                  int& h_valid, const int cpad = 0) {
+                                                  int& h_valid, __half2& omax, const int cpad = 0) {
   constexpr bool kDeconv = MODE == U16_DECONV || u16_is_ph(MODE);
 #ifdef TIC_DEBUG_SKIP_EPILOGUE  // measurement aid: time the kernels without their epilogue work
   return;
@@ -405,7 +420,7 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
       }
       uint32_t hp[8], lp[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i]);
+      for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[i], omax);
       uint4* oh = reinterpret_cast<uint4*>(obase + poff + c);
       uint4* ol = reinterpret_cast<uint4*>(obase + a.out_lo_off + poff + c);
       oh[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
@@ -517,6 +532,8 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
               __half* pl8 = reinterpret_cast<__half*>(&ql);
 #pragma unroll
               for (int e = 0; e < 8; ++e) split16(v[i + e], ph8[e], pl8[e]);
+#pragma unroll
+              for (int e = 0; e < 8; e += 2) ovf_track(omax, __halves2half2(ph8[e], ph8[e + 1]));
               *reinterpret_cast<uint4*>(oh + i) = qh;
               *reinterpret_cast<uint4*>(ol + i) = ql;
             }
@@ -563,7 +580,7 @@ __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, c
                                                            const uint32_t tbuf, const int n, const int yt, const int xt,
                                                            const bool valid, const float* s_bias, const uint32_t stage,
                                                            const int lane, const int cpad, uint64_t* rel_bar,
-                                                           const int rel_kind) {
+                                                           const int rel_kind, __half2& omax) {
   constexpr bool kPh = u16_is_ph(MODE);
   constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane: 2 | 4 | 8
   constexpr int MSH = M == 2 ? 1 : (M == 4 ? 2 : 3);
@@ -651,7 +668,7 @@ __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, c
         }
         uint32_t hp[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[px][ci][i]);
+        for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[i], lp[px][ci][i], omax);
         sts128(sp + (uint32_t)(((2 * ci) ^ sw) << 4), hp[0], hp[1], hp[2], hp[3]);
         sts128(sp + (uint32_t)(((2 * ci + 1) ^ sw) << 4), hp[4], hp[5], hp[6], hp[7]);
       }
@@ -668,7 +685,7 @@ __device__ __forceinline__ void u16_epilogue_tile_staged_t(const LayerArgs& a, c
         const int base = __shfl_sync(0xffffffffu, my_off16, owner);
         const int sw = (sp_ix >> FSH) & (M - 1);
         const uint4 val = lds128(stage + (uint32_t)((sp_ix * M + (cq ^ sw)) << 4));
-        if (base >= 0 && !(a.dbg & 8)) plane[(long long)base + row_off16 + (kPh ? (sp_ix & 1) * row16 : 0) + cq] = val;
+        if (base >= 0 && !(TIC_DBG_BITS(a.dbg) & 8)) plane[(long long)base + row_off16 + (kPh ? (sp_ix & 1) * row16 : 0) + cq] = val;
       }
       __syncwarp();
     };
@@ -692,16 +709,16 @@ template <int MODE>
 __device__ __forceinline__ void u16_epilogue_tile_staged(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
                                                          const uint32_t tbuf, const int n, const int yt, const int xt,
                                                          const bool valid, const float* s_bias, uint8_t* stage, const int lane,
-                                                         const int cpad, uint64_t* rel_bar, const int rel_kind) {
+                                                         const int cpad, uint64_t* rel_bar, const int rel_kind, __half2& omax) {
   // rel_bar: the tile buffer's `acc_empty` barrier, arrived on (rel_kind 1: this CTA's, 2: the pair leader's) by lane 0
   // right after the tile's last TMEM read
   if (MODE == U16_DECONV_RGB) return;
   const int cend = u16_is_ph(MODE) ? cpad : NPAD;
   const uint32_t st = ptx::smem_u32(stage);
   if (cend == 32)
-    u16_epilogue_tile_staged_t<MODE, 32>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind);
+    u16_epilogue_tile_staged_t<MODE, 32>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind, omax);
   else if (cend == 16)
-    u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind);
+    u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind, omax);
 }
 
 // KS = MMAs (K = 16) per tap and K-block, compile-time: with a run-time bound the unrolled body carries four
@@ -879,6 +896,7 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const int grp = m >> 3, xx = m & 7;
     const int hh = grp / p.bn, nb = grp % p.bn;
     int h_ones = 0, h_valid = 0;
+    __half2 omax = __floats2half2_rn(0.f, 0.f);
     uint32_t ti = 0;
     for (long long tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++ti) {
       if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
@@ -896,14 +914,15 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
       if (p.staged) {
         u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
-                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 1);
+                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 1, omax);
         continue;  // the staged epilogue released the buffer itself
       }
-      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
+      u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, omax, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[b]);
     }
+    if (ovf_hit(omax)) ovf_raise(a.oflow);
     // symbol histogram (quantising layers): reduce the epilogue warps through shared memory
     if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
       if (a.q == 2) {
@@ -1020,7 +1039,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 #pragma unroll
         for (int pl0 = 0; pl0 < 2; pl0 += PPS) {
           ptx::mbar_wait(&bars->empty[s], sph);
-          if (p.dbg & 2) {
+          if (TIC_DBG_BITS(p.dbg) & 2) {
             if (leader && ptx::elect_one()) ptx::mbar_arrive(&bars->full[s]);
           } else if (ptx::elect_one()) {
             if (leader) ptx::mbar_expect_tx(&bars->full[s], (uint32_t)PPS * 2u * p.box_bytes * (uint32_t)p.nbox);
@@ -1068,7 +1087,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           for (int pl0 = 0; pl0 < 2; pl0 += PPS) {
             ptx::mbar_wait(&bars->full[s], sph);
             ptx::tc_fence_after();
-            if (!(p.dbg & 1) && ptx::elect_one()) {
+            if (!(TIC_DBG_BITS(p.dbg) & 1) && ptx::elect_one()) {
 #pragma unroll
               for (int q = 0; q < PPS; ++q) {
                 const int plane = pl0 + q;
@@ -1103,6 +1122,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     const int grp = m >> 3, xx = m & 7;
     const int hh = grp / p.bn, nb = grp % p.bn;
     int h_ones = 0, h_valid = 0;
+    __half2 omax = __floats2half2_rn(0.f, 0.f);
     uint32_t ti = 0;
     for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
       if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
@@ -1118,17 +1138,18 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int yt = (int)ty * p.bh + hh, xt = (int)tx * 8 + xx;
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
-      if (p.dbg & 4) {
+      if (TIC_DBG_BITS(p.dbg) & 4) {
       } else if (p.staged) {
         u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
-                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 2);
+                                       s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 2, omax);
         continue;  // the staged epilogue released the buffer itself
       } else
-        u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, p.cpad);
+        u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, omax, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&bars->acc_empty[b]);
     }
+    if (ovf_hit(omax)) ovf_raise(a.oflow);
     if (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32) {
       if (a.q == 2) {
         h_ones = __reduce_add_sync(0xffffffffu, h_ones);
@@ -1178,11 +1199,10 @@ template <int MODE>
 inline cudaError_t u16_launch_t(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
                                 const LayerArgs& a, int grid, size_t smem) {
   auto k = u16_conv_kernel<MODE>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrCache cache;
+  {
+    cudaError_t e = cache.ensure(reinterpret_cast<const void*>(k), smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   k<<<grid, kU16Threads, smem, stream>>>(th, tl, p, a);
   return cudaGetLastError();
@@ -1192,11 +1212,10 @@ template <int MODE, int PPS>
 inline cudaError_t u16_launch_pair_pps(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
                                        const LayerArgs& a, int grid, size_t smem) {
   auto k = u16_pair_kernel<MODE, PPS>;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static SmemAttrCache cache;
+  {
+    cudaError_t e = cache.ensure(reinterpret_cast<const void*>(k), smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   k<<<grid, kU16Threads, smem, stream>>>(th, tl, p, a);  // __cluster_dims__(2, 1, 1): grid is even
   return cudaGetLastError();
@@ -1326,20 +1345,11 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   // The accumulator hand-over (tcgen05.commit -> epilogue wake-up -> cross-CTA arrive -> issuer wake-up) is ~1400
   // cycles; with two buffers that alone is ~700 cycles per tile (TIC_DBG=7 skeleton: 0.96 of decode_0's 1.95 ms).
   {
-    static const int maxbuf = [] {
-      const char* e = getenv("TIC_MAX_NBUF");
-      return e ? atoi(e) : 4;
-    }();
+    const int maxbuf = tic_env_int("TIC_MAX_NBUF", 4);  // -DTIC_ABLATE builds only
     while (p.nbuf > maxbuf && p.nbuf > 1) p.nbuf /= 2;
   }
   p.nbshift = p.nbuf == 4 ? 2 : (p.nbuf == 2 ? 1 : 0);
-  {
-    static const int dbg = [] {
-      const char* e = getenv("TIC_DBG");
-      return e ? atoi(e) : 0;
-    }();
-    p.dbg = dbg;
-  }
+  p.dbg = tic_env_int("TIC_DBG", 0);  // -DTIC_ABLATE builds only
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
   p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad) ? 1 : 0;
   const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
@@ -1362,15 +1372,12 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
   auto encode = umma_encode_fn();
   if (!encode) return fail("cuTensorMapEncodeTiled is unavailable (driver too old?)", -2);
   // widest output-channel slice whose weights stay resident
-  static const bool pair_enabled = [] {
-    const char* e = getenv("TIC_U16_PAIR");
-    return !(e && e[0] == '0');
-  }();
+  const bool pair_enabled = tic_env_int("TIC_U16_PAIR", 1) != 0;  // -DTIC_ABLATE builds only
   const bool pair = pair_enabled && num_sms >= 2;
   U16Plan plan{};
   int cs = std::min(a.cout, 128);
   // (64-channel transposed conv as two phase-stacked 32-channel slices measured slower than tap-based: 0.51 vs 0.43 ms)
-  if (kind == 1 && getenv("TIC_DECONV_PH_SLICES") != nullptr) cs = std::min(cs, 32);
+  if (kind == 1 && tic_env_set("TIC_DECONV_PH_SLICES")) cs = std::min(cs, 32);
   cs = (cs + 15) / 16 * 16;
   bool ok = false;
   for (; cs >= 16; cs -= 16)

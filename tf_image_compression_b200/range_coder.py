@@ -28,6 +28,12 @@ _SIG = {
     "tic_rc_decoder_close": (C.c_int, [C.c_void_p]),
     "tic_rc_decoder_free": (None, [C.c_void_p]),
     "tic_rc_prob_to_cum_freq": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]),
+    "tic_rc_max_encoded_bytes": (C.c_int64, [C.c_int64]),
+    "tic_rc_encode_streams": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int]),
+    "tic_rc_decode_streams": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_int]),
+    "tic_rc_crc32c": (C.c_uint32, [C.c_void_p, C.c_uint64]),
 }
 ERR_IO, ERR_TABLE, ERR_SYMBOL, ERR_CLOSED = -1, -2, -3, -4
 
@@ -54,7 +60,7 @@ def _table(cum_freq):
     for v in vals:
         if v < 0 or v >= 2 ** 32:
             raise OverflowError("cumulative frequencies must fit into an unsigned 32-bit integer")
-    return np.asarray(vals, dtype=np.uint32)
+    return np.asarray(vals, dtype=np.uint32)  # totals above 2^16 are a ValueError from the C side (include/tic_rc_core.h)
 
 
 def _raise(rc, what):
@@ -149,6 +155,63 @@ class RangeDecoder:
                 self._h = None
         except Exception:
             pass
+
+
+def encode_streams(streams, cumFreq, threads=0):
+    """Code many whole streams at once on a thread pool (one per image in encode.py's loop, :152-202, "To be
+    paralleled"): `streams` is a list of uint8 arrays (or one 2-D uint8 array, one stream per row).  Returns a list of
+    `bytes`, each exactly what RangeEncoder(path).encode(stream, cumFreq); close() writes to its file."""
+    lib = load()
+    cum = _table(cumFreq)
+    if isinstance(streams, np.ndarray) and streams.ndim == 2 and streams.dtype == np.uint8:
+        sym = np.ascontiguousarray(streams).reshape(-1)
+        lens = np.full(streams.shape[0], streams.shape[1], dtype=np.int64)
+    else:
+        arrs = [np.ascontiguousarray(np.asarray(s, dtype=np.uint8)).reshape(-1) for s in streams]
+        lens = np.asarray([a.size for a in arrs], dtype=np.int64)
+        sym = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
+    n = int(lens.size)
+    soff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=soff[1:])
+    caps = np.asarray([lib.tic_rc_max_encoded_bytes(int(v)) for v in lens], dtype=np.int64)
+    ooff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(caps, out=ooff[1:])
+    out = np.empty(int(ooff[-1]), dtype=np.uint8)
+    nbytes = np.zeros(n, dtype=np.int64)
+    rc = lib.tic_rc_encode_streams(sym.ctypes.data, soff.ctypes.data, n, cum.ctypes.data, cum.size, out.ctypes.data,
+                                   ooff.ctypes.data, nbytes.ctypes.data, int(threads))
+    if rc != 0:
+        _raise(rc, "encode_streams")
+    return [out[int(ooff[i]):int(ooff[i] + nbytes[i])].tobytes() for i in range(n)]
+
+
+def decode_streams(blobs, sizes, cumFreq, threads=0):
+    """Decode many whole streams at once (decode.py:171-208 over a directory): blobs[i] holds sizes[i] symbols.
+    Returns a list of uint8 arrays."""
+    lib = load()
+    cum = _table(cumFreq)
+    n = len(blobs)
+    lens = np.asarray([len(b) for b in blobs], dtype=np.int64)
+    ioff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=ioff[1:])
+    data = np.frombuffer(b"".join(bytes(b) for b in blobs), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    if data.size == 0:
+        data = np.zeros(1, np.uint8)
+    sizes = np.asarray(sizes, dtype=np.int64)
+    soff = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(sizes, out=soff[1:])
+    sym = np.empty(int(soff[-1]), dtype=np.uint8)
+    rc = lib.tic_rc_decode_streams(data.ctypes.data, ioff.ctypes.data, lens.ctypes.data, n, cum.ctypes.data, cum.size,
+                                   sym.ctypes.data, soff.ctypes.data, int(threads))
+    if rc != 0:
+        _raise(rc, "decode_streams")
+    return [sym[int(soff[i]):int(soff[i + 1])] for i in range(n)]
+
+
+def crc32c(data) -> int:
+    """CRC-32C (Castagnoli) of a bytes-like object (tic_rc_crc32c, host-only library)."""
+    b = bytes(data)
+    return int(load().tic_rc_crc32c(b, len(b)))
 
 
 def prob_to_cum_freq(prob, resolution=1024):

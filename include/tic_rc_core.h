@@ -46,7 +46,7 @@ typedef struct tic_rc_enc_state {
   uint64_t low;
   uint32_t range;
   uint32_t cache;
-  uint64_t pending;  /* LZMA's cacheSize: 1 + number of 0xFF bytes waiting for a possible carry */
+  uint32_t pending;  /* LZMA's cacheSize: 1 + number of 0xFF bytes waiting for a possible carry */
   uint32_t skip;     /* leading shipped bytes still to drop (2 at the start) */
 } tic_rc_enc_state;
 
@@ -90,6 +90,24 @@ template <class Sink>
 TIC_RC_HD void tic_rc_enc_step(tic_rc_enc_state* s, Sink& out, uint32_t r, uint32_t lo, uint32_t hi) {
   s->low += (uint64_t)r * lo;
   s->range = r * (hi - lo);
+  while (s->range < TIC_RC_TOP) {
+    tic_rc_shift_low(s, out);
+    s->range <<= 8;
+  }
+}
+
+/* binary alphabet, total = 2^k (every shipped config: quan_scale = 2, resolution = 4096): cum = [0, c1, 2^k].
+ * Identical arithmetic to tic_rc_enc_step with r = range >> k; r * (2^k - c1) is (r << k) - r * c1: one multiply. */
+template <class Sink>
+TIC_RC_HD void tic_rc_enc_bit(tic_rc_enc_state* s, Sink& out, uint32_t bit, int k, uint32_t c1) {
+  const uint32_t r = s->range >> k;
+  const uint32_t t = r * c1;
+  if (bit) {
+    s->low += t;
+    s->range = (r << k) - t;
+  } else {
+    s->range = t;
+  }
   while (s->range < TIC_RC_TOP) {
     tic_rc_shift_low(s, out);
     s->range <<= 8;

@@ -106,6 +106,16 @@ int encode_symbols(tic_rc_enc_state* st, Sink& out, const T* sym, int64_t n, con
   const int64_t nsym = n_cum - 1;
   const bool p2 = is_pow2(total);
   const int k = p2 ? log2u(total) : 0;
+  if (nsym == 2 && p2 && cum[1] != 0 && cum[1] != total) {
+    // binary alphabet with a power-of-two total (quan_scale = 2, resolution = 4096): the path the GPU stage runs
+    const uint32_t c1 = cum[1];
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t s = (int64_t)sym[i];
+      if (s < 0 || s > 1) return TIC_RC_ERR_SYMBOL;
+      tic_rc_enc_bit(st, out, (uint32_t)s, k, c1);
+    }
+    return TIC_RC_OK;
+  }
   for (int64_t i = 0; i < n; ++i) {
     const int64_t s = (int64_t)sym[i];
     if (s < 0 || s >= nsym) return TIC_RC_ERR_SYMBOL;

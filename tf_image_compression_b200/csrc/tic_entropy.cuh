@@ -105,27 +105,27 @@ __global__ void __launch_bounds__(32) rc_encode_kernel(const uint8_t* __restrict
     const uint4* s16 = reinterpret_cast<const uint4*>(s);
     const long long nblk = stream_len >> 4;
     uint4 nxt = nblk ? __ldg(s16) : make_uint4(0u, 0u, 0u, 0u);
+    // The symbol loop is deliberately NOT unrolled: one warp runs alone on its scheduler, so what counts is the dependent
+    // chain of a symbol (shift, multiply, select, compare) and an instruction footprint that stays inside the
+    // instruction cache (the fully unrolled 16-symbol body was 66 KB of SASS and ran at ~95 cycles per symbol).
     for (long long b = 0; b < nblk; ++b) {
-      const uint4 cur = nxt;
+      uint4 cur = nxt;
       if (b + 1 < nblk) nxt = __ldg(s16 + b + 1);
-      const uint32_t w[4] = {cur.x, cur.y, cur.z, cur.w};
       // symbols other than 0 / 1, or of zero width, are an error (checked once per block, outside the critical path)
-      const uint32_t any = w[0] | w[1] | w[2] | w[3], all = w[0] & w[1] & w[2] & w[3];
+      const uint32_t any = cur.x | cur.y | cur.z | cur.w, all = cur.x & cur.y & cur.z & cur.w;
       if (any & 0xFEFEFEFEu) bad = 1;
       if ((any && w1 == 0) || ((~all & 0x01010101u) && c1 == 0)) bad = 1;
       if (bad) break;
-#pragma unroll
+#pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-#pragma unroll
+        uint32_t word = cur.x;
+        cur.x = cur.y;
+        cur.y = cur.z;
+        cur.z = cur.w;
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-          const uint32_t one = (w[i] >> (8 * j)) & 1u;
-          const uint32_t r = st.range >> k;
-          if (one) st.low += (uint64_t)r * c1;
-          st.range = r * (one ? w1 : c1);
-          while (st.range < TIC_RC_TOP) {
-            tic_rc_shift_low(&st, sink);
-            st.range <<= 8;
-          }
+          tic_rc_enc_bit(&st, sink, word & 1u, k, c1);
+          word >>= 8;
         }
       }
     }
@@ -174,19 +174,24 @@ __global__ void __launch_bounds__(32) rc_decode_kernel(const uint8_t* __restrict
     const uint32_t c1 = s_cum[1];
     uint4* o16 = reinterpret_cast<uint4*>(o);
     for (long long b = 0; b < (stream_len >> 4); ++b) {
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
+      uint4 o4 = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
       for (int i = 0; i < 4; ++i) {
-#pragma unroll
+        uint32_t word = 0u;
+#pragma unroll 1
         for (int j = 0; j < 4; ++j) {
           const uint32_t r = st.range >> k;
           const uint32_t t = r * c1;
           const bool one = c1 == total ? false : st.code >= t;
-          w[i] |= (one ? 1u : 0u) << (8 * j);
+          word |= (one ? 1u : 0u) << (8 * j);
           tic_rc_dec_step(&st, src, r, one ? c1 : 0u, one ? total : c1);
         }
+        o4.x = o4.y;
+        o4.y = o4.z;
+        o4.z = o4.w;
+        o4.w = word;
       }
-      o16[b] = make_uint4(w[0], w[1], w[2], w[3]);
+      o16[b] = o4;
     }
   } else {
     for (long long i = 0; i < stream_len; ++i) {

@@ -692,19 +692,26 @@ constexpr uint32_t kRawStageF32 = 7424;            // 33 * 224 = 7392, padded to
 constexpr int kRawStagesF32 = 4;
 constexpr int kT2Stages = 6;                       // operand stages = raw-window stages = builder warps (warp w owns slot w)
 
+// The stage of a warp is the TMA-store image of its 32 pixels = rows [y0, y0 + 4) x columns [x0, x0 + 8) of the tile:
+// [4][8][CEND] halves per plane, 16-byte chunks XOR-swizzled exactly like CU_TENSOR_MAP_SWIZZLE_64B (CEND = 32) /
+// _32B (CEND = 16) of the output tensor maps (chunk ^= (pixel >> FSH) & (M - 1): the pattern is a function of the
+// shared-memory address bits, the stage is 1024-byte aligned).  One lane ships both planes with two
+// cp.async.bulk.tensor stores (UTMASTG): no shared-memory read-back, no per-lane global stores.
 template <int CEND>
-__device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const uint32_t tbuf, const int NPAD, const int n, const int yt,
-                                                     const int xt, const float* s_bias, const uint32_t stage, const int lane,
+__device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const CUtensorMap* tm_ohi, const CUtensorMap* tm_olo,
+                                                     const uint32_t tbuf, const int NPAD, const int n, const int y0, const int x0,
+                                                     const float* s_bias, const uint32_t stage, const int lane,
                                                      uint64_t* rel_bar, __half2& omax) {
   constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane
   constexpr int MSH = M == 2 ? 1 : 2;
   constexpr int FSH = 3 - MSH;                       // swizzle: chunk ^= (pixel >> FSH) & (M - 1)
   constexpr int NCI = CEND / 16;
   const float floor_v = a.act ? 0.0f : -INFINITY;
-  const long long pix0 = ((long long)n * a.hout + yt) * a.wout + xt;
-  const int my_off16 = (int)((pix0 * a.cout * 2) >> 4);   // this lane's pixel row inside a plane, 16-byte units
   const uint32_t sp = stage + (uint32_t)lane * (M * 16);
   const int sw = (lane >> FSH) & (M - 1);
+  // the stores of this warp's previous tile have read the stage (they had a whole tile period for it)
+  if (lane == 0) ptx::bulk_wait_group_read<0>();
+  __syncwarp();
 #pragma unroll
   for (int ci = 0; ci < NCI; ++ci) {
     float v[16], u[16];
@@ -733,24 +740,13 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const u
     sts128(sp + kT2LoOff + (uint32_t)(((2 * ci) ^ sw) << 4), lp[0], lp[1], lp[2], lp[3]);
     sts128(sp + kT2LoOff + (uint32_t)(((2 * ci + 1) ^ sw) << 4), lp[4], lp[5], lp[6], lp[7]);
   }
+  ptx::fence_proxy_async_smem();  // generic-proxy stage writes -> visible to the TMA store
   __syncwarp();
-  // write back: chunk q of the stage -> its pixel's row; a warp's 8-pixel rows are contiguous 512-byte (M = 4) runs
-  uint4* const ohi = reinterpret_cast<uint4*>(a.out);
-  uint4* const olo = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(a.out) + a.out_lo_off);
-#pragma unroll
-  for (int j = 0; j < M; ++j) {
-    const int q = lane + 32 * j;
-    const int px = q >> MSH, cq = q & (M - 1);
-    const int base = __shfl_sync(0xffffffffu, my_off16, px);
-    const int swq = (px >> FSH) & (M - 1);
-    const uint32_t src = stage + (uint32_t)((px * M + (cq ^ swq)) << 4);
-    const uint4 vh = lds128(src), vl = lds128(src + kT2LoOff);
-    if (!(TIC_DBG_BITS(a.dbg) & 8)) {
-      ohi[(long long)base + cq] = vh;
-      olo[(long long)base + cq] = vl;
-    }
+  if (lane == 0 && !(TIC_DBG_BITS(a.dbg) & 8)) {
+    ptx::tma_store_4d_s(tm_ohi, stage, 0, x0, y0, n);
+    ptx::tma_store_4d_s(tm_olo, stage + kT2LoOff, 0, x0, y0, n);
+    ptx::bulk_commit_group();
   }
-  __syncwarp();
 }
 
 // (x - mean) / std for a launch-constant std without the division routine (~15 instructions, 12 per builder thread
@@ -765,7 +761,8 @@ __device__ __forceinline__ float f16_norm_fast(float x, float mean, float stdv, 
 
 template <bool F32>
 __global__ void __launch_bounds__(kT2Threads, 1)
-f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Params p, const LayerArgs a) {
+f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_ohi,
+                        const __grid_constant__ CUtensorMap tm_olo, const F16Params p, const LayerArgs a) {
   constexpr uint32_t RAW_ROW = F32 ? kRawRowF32 : kRawRow, RAW_STAGE = F32 ? kRawStageF32 : kRawStage;
   constexpr uint32_t RAW_STAGES = kT2Stages;
   const int NPAD = p.npad;
@@ -777,15 +774,19 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
   uint8_t* s_rawwin = s_stage + kT2EpiWarps * kT2StagePerWarp;
   W2SmemBars* bars = reinterpret_cast<W2SmemBars*>(s_rawwin + RAW_STAGES * RAW_STAGE);
   __shared__ __align__(16) float s_bias[128];
-  __shared__ uint32_t s_plut[3 * 256];
+  // u8 -> (hi | lo' << 16) of the normalised value, kLutRep interleaved copies: lane l reads copy l % kLutRep, so two lanes
+  // only share a bank when they are the same copy AND their bytes agree modulo 32 / kLutRep (the byte-indexed look-ups
+  // were 60 % of this kernel's shared-load wavefronts as bank conflicts, profiles/r1g_summary_f16x3.md)
+  constexpr int kLutRep = 8;
+  __shared__ uint32_t s_plut[3 * 256 * kLutRep];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid < 128) s_bias[tid] = (tid < NPAD && tid < a.cout) ? a.bias[tid] : 0.f;
   if (!F32)
-    for (int i = tid; i < 3 * 256; i += kT2Threads) {
+    for (int i = tid; i < 3 * 256 * kLutRep; i += kT2Threads) {
       __half hi, lo;
-      split16(a.lut[i], hi, lo);
+      split16(a.lut[i / kLutRep], hi, lo);
       s_plut[i] = pack_half2(hi, lo);
     }
   for (int i = tid; i < 12 * NPAD; i += kT2Threads)
@@ -821,6 +822,9 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     // (row, quad of 4 pixels) items of a tile are six independent passes per lane, so the shared-memory latencies of
     // one pass hide under the next (six warps in lock-step on one tile ran at 12 cycles per instruction) =====
     const float rstd0 = __frcp_rn(a.stdv[0]), rstd1 = __frcp_rn(a.stdv[1]), rstd2 = __frcp_rn(a.stdv[2]);
+    const uint32_t* const plut0 = s_plut + (lane & (kLutRep - 1));
+    const uint32_t* const plut1 = plut0 + 256 * kLutRep;
+    const uint32_t* const plut2 = plut1 + 256 * kLutRep;
     const uint32_t slot = (uint32_t)warp;
     const uint8_t* rawb = s_rawwin + (size_t)slot * RAW_STAGE;
     uint8_t* stb = s_a + (size_t)slot * 10240;
@@ -872,9 +876,9 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
               const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
               const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
               const bool okj = iy < p.P && ix + j < p.P;
-              const uint32_t x0 = okj ? s_plut[b0] : 0u;
-              const uint32_t x1 = okj ? s_plut[256 + b1] : 0u;
-              const uint32_t x2 = okj ? s_plut[512 + b2] : 0u;
+              const uint32_t x0 = okj ? plut0[b0 * kLutRep] : 0u;
+              const uint32_t x1 = okj ? plut1[b1 * kLutRep] : 0u;
+              const uint32_t x2 = okj ? plut2[b2 * kLutRep] : 0u;
               vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
               vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
             }
@@ -960,10 +964,12 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
     // ===== epilogue: group g = TMEM buffer g = tiles it % 4 == g =====
     const int ew = warp - kT2EpiWarp0;
     const int q4 = warp & 3, group = ew >> 2;
-    const int m = q4 * 32 + lane;
-    const int hh = m >> 3, xx = m & 7;
     const uint32_t stage = ptx::smem_u32(s_stage + (size_t)ew * kT2StagePerWarp);
     const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)group * pairw;
+    if (lane == 0) {
+      ptx::prefetch_tmap(&tm_ohi);
+      ptx::prefetch_tmap(&tm_olo);
+    }
     uint32_t use = 0;
     __half2 omax = __floats2half2_rn(0.f, 0.f);
     for (long long tile = blockIdx.x + (long long)group * gridDim.x; tile < p.num_tiles; tile += 4LL * gridDim.x, ++use) {
@@ -977,10 +983,13 @@ f16_first_s2_tma_kernel(const __grid_constant__ CUtensorMap tm_img, const F16Par
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bars->acc_empty[group]);
       } else if (NPAD == 32)
-        f16_t2_epilogue_tile<32>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group], omax);
+        f16_t2_epilogue_tile<32>(a, &tm_ohi, &tm_olo, tbuf, NPAD, (int)tn, (int)ty * 16 + 4 * q4, (int)tx * 8, s_bias, stage, lane,
+                                 &bars->acc_empty[group], omax);
       else
-        f16_t2_epilogue_tile<16>(a, tbuf, NPAD, (int)tn, (int)ty * 16 + hh, (int)tx * 8 + xx, s_bias, stage, lane, &bars->acc_empty[group], omax);
+        f16_t2_epilogue_tile<16>(a, &tm_ohi, &tm_olo, tbuf, NPAD, (int)tn, (int)ty * 16 + 4 * q4, (int)tx * 8, s_bias, stage, lane,
+                                 &bars->acc_empty[group], omax);
     }
+    if (lane == 0) ptx::bulk_wait_group<0>();  // every store of this warp is complete before the CTA may exit
     if (ovf_hit(omax)) ovf_raise(a.oflow);
   }
 
@@ -1107,10 +1116,27 @@ inline int launch_first16(cudaStream_t stream, const LayerArgs& a, int stride, c
     if (cache_t2u.ensure(reinterpret_cast<const void*>(f16_first_s2_tma_kernel<false>), big) != cudaSuccess ||
         cache_t2f.ensure(reinterpret_cast<const void*>(f16_first_s2_tma_kernel<true>), big) != cudaSuccess)
       return fail("cudaFuncSetAttribute(first-layer TMA kernel) failed", -2);
+    // output tensor maps (hi / lo' plane of the NHWC pair-plane activation): box = one epilogue warp's 4 rows x 8 columns
+    CUtensorMap tm_o[2];
+    {
+      auto encode = umma_encode_fn();
+      const cuuint64_t C = a.cout, Wd = a.wout, Hd = a.hout, Nd = a.n;
+      cuuint64_t dims[4] = {C, Wd, Hd, Nd};
+      cuuint64_t strides[3] = {C * 2, Wd * C * 2, Hd * Wd * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)a.cout, 8, 4, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      for (int pl = 0; pl < 2; ++pl) {
+        void* base = reinterpret_cast<__half*>(a.out) + (pl ? a.out_lo_off : 0);
+        CUresult r = encode(&tm_o[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            a.cout == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (first-layer output) failed (" + std::to_string((int)r) + ")", -2);
+      }
+    }
     if (f32in)
-      f16_first_s2_tma_kernel<true><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
+      f16_first_s2_tma_kernel<true><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, tm_o[0], tm_o[1], p, a);
     else
-      f16_first_s2_tma_kernel<false><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, p, a);
+      f16_first_s2_tma_kernel<false><<<grid, kT2Threads, smem_t2, stream>>>(tm_img, tm_o[0], tm_o[1], p, a);
   } else if (windowed)
     f16_first_s2_kernel<<<grid, kW2Threads, smem_w2, stream>>>(tm_img, p, a);
   else if (stride == 1)

@@ -1,7 +1,25 @@
 """PCIe rates of the box with pinned host memory: H2D alone, D2H alone, both directions at once (what bounds the
-host-to-host round trip: 604 MB in, 654 MB out per 64 images)."""
+host-to-host round trip: 604 MB in, 654 MB out per 64 images).  Under torchrun every rank drives its own GPU AT THE
+SAME TIME (barrier before every timed repetition) and rank 0 prints the per-rank mean and the aggregate over the box:
+the bound of the N-GPU end-to-end numbers, whose ranks share the host's memory and PCIe fabric."""
+import os
 import time
+
 import torch
+
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+if world > 1:
+    import torch.distributed as dist
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))  # like bench.py
+    except Exception:
+        pass
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
 n = 604 * 1024 * 1024
 h_in = torch.empty(n, dtype=torch.uint8).pin_memory()
@@ -11,11 +29,19 @@ d_b = torch.empty(n, dtype=torch.uint8, device="cuda")
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
 
+def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
 def best(fn, reps=5):
     fn()
-    torch.cuda.synchronize()
+    barrier()
     t = 1e9
     for _ in range(reps):
+        barrier()
         t0 = time.perf_counter()
         fn()
         torch.cuda.synchronize()
@@ -38,9 +64,16 @@ def both():
     d2h()
 
 
-t = best(h2d)
-print(f"H2D alone  {n / t / 1e9:6.1f} GB/s")
-t = best(d2h)
-print(f"D2H alone  {n / t / 1e9:6.1f} GB/s")
-t = best(both)
-print(f"both       {n / t / 1e9:6.1f} GB/s per direction ({2 * n / t / 1e9:.1f} GB/s total)")
+def report(name, t, factor=1):
+    rate = torch.tensor([factor * n / t / 1e9], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rate)
+    if rank == 0:
+        print(f"{name:10s} {rate.item() / world:6.1f} GB/s per GPU, {rate.item():7.1f} GB/s over {world} GPU(s) at once")
+
+
+report("H2D alone", best(h2d))
+report("D2H alone", best(d2h))
+report("both", best(both), 2)
+if world > 1:
+    dist.destroy_process_group()

@@ -15,6 +15,7 @@
 #include "tic_umma16.cuh"
 #include "tic_first16.cuh"
 #include "tic_fused16.cuh"
+#include "tic_fused_enc16.cuh"
 #include "tic_entropy.cuh"
 
 using namespace tic;
@@ -31,6 +32,7 @@ struct Layer {
   U16Weights uw16;        // fp16-pair operand images
   F16Weights fw16;        // fp16-pair first-layer (cin = 3) operand image
   FusedDecWeights fdw;    // operand images of this layer and the next one for the fused transposed-conv pair
+  FusedEncWeights few;    // ... for the fused first two layers of an encoder
   bool loaded = false;
 };
 
@@ -573,6 +575,37 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
             fused = true;
           }
         }
+        // ... and the first two layers of an encoder (u8 image -> 3 -> 32 -> 32, both stride 2): tic_fused_enc16.cuh
+        if (!fused && pair16 && first_group && i == 0 && cur < 0 && i + 1 < G.last && !g.layers[1].d.res_begin && !g.layers[1].d.res_end &&
+            tic_env_int("TIC_FUSE_ENC", 1) != 0) {
+          Layer& ly2 = g.layers[1];
+          const LayerShape& t2 = sh[1];
+          LayerArgs a2 = a;
+          a2.hin = t2.hin;
+          a2.win = t2.win;
+          a2.cin = t2.cin;
+          a2.hout = t2.hout;
+          a2.wout = t2.wout;
+          a2.cout = t2.cout;
+          a2.pad_t = t2.pad_t;
+          a2.pad_l = t2.pad_l;
+          a2.act = ly2.d.act;
+          a2.wgt = ly2.w;
+          a2.bias = ly2.b;
+          a2.res = nullptr;
+          a2.in = nullptr;
+          a2.in_mode = IO_ACT16;
+          a2.out_mode = IO_ACT16;
+          a2.out = h->act[0];
+          a2.out_lo_off = (long long)ns * t2.hout * t2.wout * t2.cout;
+          if (fused_enc_supported(a, d.kind, d.stride, a2, ly2.d.kind, ly2.d.stride)) {
+            int nl = 0;
+            rc = launch_fused_enc(h->stream, a, a2, ly.w, ly2.w, &ly.few, h->num_sms, &h->err, &nl);
+            h->launches += nl;
+            fused = true;
+            ob = 0;  // the pair's output lives in act[0]
+          }
+        }
         if (fused) {
           ++i;  // the next layer ran inside this launch (its time is reported with this layer)
         } else if (pair16 && f16_first_supported(a, d.kind, d.stride)) {
@@ -840,6 +873,7 @@ void tic_destroy(tic_codec* h) {
       l.uw16.release();
       l.fw16.release();
       l.fdw.release();
+      l.few.release();
     }
     if (h->g[gi].d_normlut) cudaFree(h->g[gi].d_normlut);
   }
@@ -945,6 +979,7 @@ int tic_set_graph(tic_codec* h, int graph, const tic_layer_desc* layers, int n_l
     l.uw16.release();
     l.fw16.release();
     l.fdw.release();
+    l.few.release();
   }
   g.layers.assign(n_layers, Layer());
   for (int i = 0; i < n_layers; ++i) {
@@ -981,7 +1016,11 @@ int tic_load_weights(tic_codec* h, int graph, int layer, const float* kernel, co
   l.uw16.release();
   l.fw16.release();
   l.fdw.release();
-  if (layer > 0) g.layers[layer - 1].fdw.release();  // the fused pair kernel keeps this layer's operand image with the previous layer
+  l.few.release();
+  if (layer > 0) {  // the fused pair kernels keep this layer's operand image with the previous layer
+    g.layers[layer - 1].fdw.release();
+    g.layers[layer - 1].few.release();
+  }
   l.loaded = true;
   return TIC_OK;
 }

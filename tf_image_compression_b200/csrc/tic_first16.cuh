@@ -701,7 +701,8 @@ template <int CEND>
 __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const CUtensorMap* tm_ohi, const CUtensorMap* tm_olo,
                                                      const uint32_t tbuf, const int NPAD, const int n, const int y0, const int x0,
                                                      const float* s_bias, const uint32_t stage, const int lane,
-                                                     uint64_t* rel_bar, __half2& omax) {
+                                                     uint64_t* rel_bar, __half2& omax, const bool rel_leader = false,
+                                                     const bool store = true) {
   constexpr int M = CEND >> 3;                       // 16-byte chunks per pixel and plane
   constexpr int MSH = M == 2 ? 1 : 2;
   constexpr int FSH = 3 - MSH;                       // swizzle: chunk ^= (pixel >> FSH) & (M - 1)
@@ -721,7 +722,12 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const C
     if (ci == NCI - 1) {  // last TMEM read of the tile: hand the buffer back
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(rel_bar);
+      if (lane == 0) {
+        if (rel_leader)
+          ptx::mbar_arrive_leader(rel_bar);   // CTA-pair kernels: the barrier lives in the leader CTA
+        else
+          ptx::mbar_arrive(rel_bar);
+      }
     }
     const float4* bp = reinterpret_cast<const float4*>(s_bias + ci * 16);
 #pragma unroll
@@ -742,7 +748,7 @@ __device__ __forceinline__ void f16_t2_epilogue_tile(const LayerArgs& a, const C
   }
   ptx::fence_proxy_async_smem();  // generic-proxy stage writes -> visible to the TMA store
   __syncwarp();
-  if (lane == 0 && !(TIC_DBG_BITS(a.dbg) & 8)) {
+  if (lane == 0 && store && !(TIC_DBG_BITS(a.dbg) & 8)) {
     ptx::tma_store_4d_s(tm_ohi, stage, 0, x0, y0, n);
     ptx::tma_store_4d_s(tm_olo, stage + kT2LoOff, 0, x0, y0, n);
     ptx::bulk_commit_group();

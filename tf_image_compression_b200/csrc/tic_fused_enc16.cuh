@@ -1,0 +1,574 @@
+// Back-to-back fused first two layers of the analysis transform (model_0/model.py:50-71: encode_0 3 -> 32 stride 2 relu on
+// the normalised u8 patch, encode_1 32 -> 32 stride 2 relu) as ONE kernel.  Unfused, the 64 x 64 x 32 tensor between them
+// (6.4 GB per 12 288 patches as fp16 pair planes) is written by the first-layer kernel and read back by the next:
+// 12.9 GB of the encoder's 16.6 GB of HBM traffic, and encode_1 sits on the HBM roofline because of it.  Here it lives
+// in shared memory only:
+//
+//   TMA (raw u8 window of the image) -> builders (normalise through the split table, RGB0 fp16 quads, tic_first16.cuh)
+//   -> MMA1 (no-im2col windowed operands, four 16 x 8 sub-tiles) -> TMEM -> epilogue 1: bias, relu, fp16 split, written as
+//   the swizzled K-major stride-2 operand tile of the next layer -> MMA2 (nine taps) -> TMEM -> epilogue 2: bias, relu,
+//   fp16 split -> pair-plane output.
+//
+// A CTA pair (cta_group::2, M = 256) walks two patches in lock-step; a step is one encode_1 output tile (16 x 8) = a
+// 32 x 16 region of the intermediate map.  The stride-2 SAME conv reads intermediate rows 2y .. 2y + 2: one halo row BELOW
+// and one halo column RIGHT of the region.  They are not recomputed: tiles are walked bottom-to-top, right-to-left, and
+// the first row / first column of every tile is kept in small shared-memory caches for the tile above / to the left
+// (zeros at the patch border = the conv's zero padding), so MMA1 does exactly the work of the unfused layer.
+//
+// Warps (832 threads, <= 78 registers): 0 raw-window TMA, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue
+// (four per TMEM lane quadrant: one first-layer sub-tile each; two of the four also take a 16-channel unit of epilogue 2
+// one tile behind), 20-25 builders.  TMEM: 4 x 64 columns for MMA1's sub-tiles, two buffers of 64 columns for MMA2.
+#pragma once
+#include "tic_first16.cuh"
+#include "tic_fused16.cuh"
+
+namespace tic {
+
+constexpr int kFEThreads = 832;
+constexpr int kFEBuilderWarp0 = 20, kFEBuilders = 6;
+constexpr int kFEOpCols = 34;                                   // input pixels per operand row: 2 * 16 + 1 halo + 1 over-read
+constexpr uint32_t kFEOpPitch = kFEOpCols * 8;                  // 272 bytes (RGB0 fp16 quads)
+constexpr int kFEOpRows = 65;                                   // 2 * 32 + 1
+constexpr uint32_t kFEOpPlane = 17920;                          // >= 65 * 272 = 17680, multiple of 256
+constexpr uint32_t kFERawRow = 112;                             // bytes per raw-window row (34 px * 3 = 102, padded to 16)
+constexpr uint32_t kFERawStage = 7424;                          // >= 65 * 112 = 7280, multiple of 128
+constexpr int kFERawStages = 2;
+constexpr uint32_t kFERegionPlane = 39936;                      // >= 17 * 2 * 9 * 128 = 39168, multiple of 1024
+constexpr int kFELutRep = 4;                                    // (8 in the stand-alone kernel; 12 KB less static shared memory here)
+constexpr uint32_t kFEStagePerWarp = 4096;                      // epilogue 2: hi | lo' plane of 32 pixels x 32 channels (TMA-store image)
+
+struct FusedEncParams {
+  int n;                    // patches
+  int P;                    // patch edge (input of encode_0)
+  int tiles_x, tiles_y;     // encode_1 output tiles per patch (16 rows x 8 columns)
+  int tiles_pp;
+  long long pairs_total;
+  const uint8_t* w1img;     // first-layer operand image, per CTA rank (f16_build_weights_s2_pair_kernel)
+  uint32_t w1_off, w2_off, w2B_off, op_off, raw_off, region_off, rowc_off, colc_off, stage_off, bars_off;
+  uint32_t smem_bytes;
+};
+
+struct FusedEncBars {
+  uint64_t w_full;
+  uint64_t raw_full[kFERawStages], raw_empty[kFERawStages];
+  uint64_t op_full, op_empty;
+  uint64_t acc1_full, acc1_empty;
+  uint64_t reg_full, reg_empty;
+  uint64_t acc2_full[2], acc2_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t fused_swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
+
+// device [9][3][32] fp32 -> per CTA rank r of the pair, per filter row kh:
+//   region A [k group (2)][32 rows][8 halves]: r = 0 -> W_hi rows, r = 1 -> W_lo' rows   (stacked product, N = 64 over the pair)
+//   region B [k group (2)][16 rows][8 halves]: W_hi rows r * 16 ...                        (A_lo' x W_hi, N = 32 over the pair)
+// k = px * 4 + c (RGB0 quads of 4 consecutive input pixels; the 4th pixel and the 4th channel are zero).
+// Layout per rank: A(kh = 0..2) 3 x 1024 B, then B(kh = 0..2) 3 x 512 B.
+__global__ void f16_build_weights_s2_pair_kernel(const float* __restrict__ w, int cout, uint8_t* __restrict__ img) {
+  const int per_rank = 3 * (2 * 32 * 8 + 2 * 16 * 8);  // halves
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += gridDim.x * blockDim.x) {
+    const int rank = i / per_rank;
+    int j = i - rank * per_rank;
+    const bool inB = j >= 3 * 2 * 32 * 8;
+    if (inB) j -= 3 * 2 * 32 * 8;
+    const int rows = inB ? 16 : 32;
+    const int e = j & 7, row = (j >> 3) % rows, kg = (j / (8 * rows)) & 1, kh = j / (16 * rows);
+    const int k = kg * 8 + e, px = k >> 2, c = k & 3;
+    const int oc = inB ? rank * 16 + row : row;
+    const float v = (px < 3 && c < 3 && oc < cout) ? w[((kh * 3 + px) * 3 + c) * cout + oc] : 0.f;
+    __half hi, lo;
+    split16(v, hi, lo);
+    const bool want_lo = !inB && rank == 1;
+    uint8_t* base = img + (size_t)rank * 4608 + (inB ? 3072 + kh * 512 : kh * 1024);
+    *reinterpret_cast<__half*>(base + (size_t)kg * (rows * 16) + (size_t)row * 16 + e * 2) = want_lo ? lo : hi;
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFEThreads, 1)
+fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_constant__ CUtensorMap tm_ohi,
+                 const __grid_constant__ CUtensorMap tm_olo, const LayerArgs a1, const U16Params p2, const LayerArgs a2,
+                 const FusedEncParams fp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* s_w1 = smem + fp.w1_off;            // 4608 B: this rank's first-layer operand image
+  uint8_t* s_w2A = smem + fp.w2_off;
+  uint8_t* s_w2B = smem + fp.w2B_off;
+  uint8_t* s_op = smem + fp.op_off;            // hi plane | lo' plane of the normalised input window (RGB0 quads)
+  uint8_t* s_rawwin = smem + fp.raw_off;
+  uint8_t* s_region = smem + fp.region_off;    // hi plane | lo' plane of the 33 x 17 intermediate region (stride-2 box layout)
+  uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][tiles_x][16 px][hi 64 B | lo 64 B]
+  uint8_t* s_colc = smem + fp.colc_off;        // [parity][32 px][hi | lo]
+  uint8_t* s_stage = smem + fp.stage_off;      // 4 x 4 KB: epilogue 2's TMA-store images (one per TMEM lane quadrant)
+  FusedEncBars* bars = reinterpret_cast<FusedEncBars*>(smem + fp.bars_off);
+  __shared__ __align__(16) float s_bias1[32];
+  __shared__ __align__(16) float s_bias2[32];
+  __shared__ uint32_t s_plut[3 * 256 * kFELutRep];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid < 32) {
+    s_bias1[tid] = tid < a1.cout ? a1.bias[tid] : 0.f;
+    s_bias2[tid] = tid < a2.cout ? a2.bias[tid] : 0.f;
+  }
+  for (int i = tid; i < 3 * 256 * kFELutRep; i += kFEThreads) {
+    __half hi, lo;
+    split16(a1.lut[i / kFELutRep], hi, lo);
+    s_plut[i] = pack_half2(hi, lo);
+  }
+  for (int i = tid; i < 4608 / 16; i += kFEThreads)
+    reinterpret_cast<uint4*>(s_w1)[i] = __ldg(reinterpret_cast<const uint4*>(fp.w1img + (size_t)rank * 4608) + i);
+  if (tid == 0) {
+    ptx::mbar_init(&bars->w_full, leader ? 2 : 1);
+    for (int i = 0; i < kFERawStages; ++i) {
+      ptx::mbar_init(&bars->raw_full[i], 1);
+      ptx::mbar_init(&bars->raw_empty[i], kFEBuilders);
+    }
+    ptx::mbar_init(&bars->op_full, 2 * kFEBuilders);
+    ptx::mbar_init(&bars->op_empty, 1);
+    ptx::mbar_init(&bars->acc1_full, 1);
+    ptx::mbar_init(&bars->acc1_empty, 2 * 16);
+    ptx::mbar_init(&bars->reg_full, 2 * 16);
+    ptx::mbar_init(&bars->reg_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars->acc2_full[i], 1);
+      ptx::mbar_init(&bars->acc2_empty[i], 2 * 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc2(&bars->tmem_base, 512);
+    ptx::tmem_relinquish2();
+  }
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const long long npairs = gridDim.x >> 1, pair0 = blockIdx.x >> 1;
+  const int NPAD2 = p2.npad;   // 32
+  long long my_pairs = fp.pairs_total > pair0 ? (fp.pairs_total - pair0 + npairs - 1) / npairs : 0;
+  const long long nsteps = my_pairs * fp.tiles_pp;
+  // step -> tile: tiles are walked bottom-to-top, right-to-left inside a patch
+  auto tile_of = [&](int t, int& ty, int& tx) {
+    const int r = fp.tiles_pp - 1 - t;
+    ty = r / fp.tiles_x;
+    tx = r - ty * fp.tiles_x;
+  };
+
+  if (warp == 0) {
+    // ===== raw-window producer (both CTAs): encode_1's weight halves once, then one 65 x 112-byte box per tile =====
+    const Geo g = a1.geo;
+    if (ptx::elect_one()) {
+      ptx::prefetch_tmap(&tm_img);
+      const uint32_t w2A = (p2.wA_bytes + 1023u) & ~1023u, w2B = (p2.wB_bytes + 1023u) & ~1023u;
+      const uint8_t* src2 = p2.wimg + (size_t)rank * (w2A + w2B);
+      ptx::mbar_expect_tx(&bars->w_full, p2.wA_bytes + p2.wB_bytes);
+      for (uint32_t off = 0; off < p2.wA_bytes; off += 16384u) ptx::bulk_load(s_w2A + off, src2 + off, min(16384u, p2.wA_bytes - off), &bars->w_full);
+      ptx::bulk_load(s_w2B, src2 + w2A, p2.wB_bytes, &bars->w_full);
+    }
+    __syncwarp();
+    if (!leader) {
+      ptx::mbar_wait(&bars->w_full, 0);
+      if (ptx::elect_one()) ptx::mbar_arrive_leader(&bars->w_full);
+      __syncwarp();
+    }
+    long long step = 0;
+    for (long long pp = pair0; pp < fp.pairs_total; pp += npairs) {
+      const long long n0 = 2 * pp + rank;
+      unsigned img = 0, gy = 0, gx = 0;
+      if (n0 < fp.n) geo_decode(g, (unsigned)(g.n0 + n0), img, gy, gx);
+      for (int t = 0; t < fp.tiles_pp; ++t, ++step) {
+        int ty, tx;
+        tile_of(t, ty, tx);
+        const uint32_t r = (uint32_t)(step % kFERawStages);
+        ptx::mbar_wait(&bars->raw_empty[r], (uint32_t)((step / kFERawStages) & 1) ^ 1u);
+        if (ptx::elect_one()) {
+          // a patch beyond the batch (odd tail): fetch image 0's window, epilogue 2 stores nothing
+          const int Yb = g.oy + (int)gy * g.P + 64 * ty, Xb = g.ox + (int)gx * g.P + 32 * tx;
+          ptx::mbar_expect_tx(&bars->raw_full[r], kFEOpRows * kFERawRow);
+          ptx::tma_load_3d(s_rawwin + (size_t)r * kFERawStage, &tm_img, &bars->raw_full[r], Xb * 3, Yb, (int)img);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader): MMA1 of tile i + 1 is issued before MMA2 of tile i =====
+    if (leader && nsteps > 0) {
+      // first layer: un-swizzled K-major operands straight over the input window (tic_first16.cuh), M = 256 over the pair
+      const uint32_t idesc1_st = ptx::make_idesc_f16(256, 64), idesc1_lo = ptx::make_idesc_f16(256, 32);
+      const uint32_t a1_hi32 = ((2u * kFEOpPitch) >> 4) | (1u << 14);
+      const uint32_t w1_hi32 = (128u >> 4) | (1u << 14);
+      const uint32_t a1_lbo = (16u >> 4) << 16;
+      const uint32_t w1A_d = (ptx::smem_u32(s_w1) >> 4) | (((32u * 16u) >> 4) << 16);           // k-group stride: 32 rows x 16 B
+      const uint32_t w1B_d = (ptx::smem_u32(s_w1 + 3072) >> 4) | (((16u * 16u) >> 4) << 16);    // 16 rows x 16 B
+      const uint32_t op_d = (ptx::smem_u32(s_op) >> 4) | a1_lbo;
+      // second layer: the stride-2 pair kernel's operand geometry over the region buffer
+      const uint32_t idesc2_st = ptx::make_idesc_f16(256, 2 * NPAD2), idesc2_lo = ptx::make_idesc_f16(256, NPAD2);
+      const uint32_t a2_hi32 = (p2.sbo >> 4) | (1u << 14) | (p2.a_layout << 29);
+      const uint32_t w2_hi32 = (p2.w_sbo >> 4) | (1u << 14) | (p2.w_layout << 29);
+      const uint32_t tap2A = (uint32_t)NPAD2 * (uint32_t)p2.kc * 2u, tap2B = tap2A >> 1;
+      const uint32_t w2A_d = (ptx::smem_u32(s_w2A) >> 4) | (1u << 16), w2B_d = (ptx::smem_u32(s_w2B) >> 4) | (1u << 16);
+      const uint32_t reg_d = (ptx::smem_u32(s_region) >> 4) | (1u << 16);
+      ptx::mbar_wait(&bars->w_full, 0);
+      auto mma1 = [&](long long step) {
+        ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u);
+        ptx::mbar_wait(&bars->op_full, (uint32_t)(step & 1));
+        ptx::tc_fence_after();
+        if (!(TIC_DBG_BITS(p2.dbg) & 16) && ptx::elect_one()) {
+#pragma unroll
+          for (int sub = 0; sub < 4; ++sub) {
+            const uint32_t aoff = ((uint32_t)((sub >> 1) * 32) * kFEOpPitch + (uint32_t)((sub & 1) * 16) * 8u) >> 4;
+            const uint32_t ah = op_d + aoff, al = ah + (kFEOpPlane >> 4);
+            const uint32_t d = tmem_base + (uint32_t)sub * 64u;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+              ptx::mma2_f16_ss(d, u16_desc(ah + (uint32_t)kh * (kFEOpPitch >> 4), a1_hi32), u16_desc(w1A_d + (uint32_t)kh * (1024u >> 4), w1_hi32),
+                               idesc1_st, kh ? 1u : 0u);
+              ptx::mma2_f16_ss(d + 32u, u16_desc(al + (uint32_t)kh * (kFEOpPitch >> 4), a1_hi32), u16_desc(w1B_d + (uint32_t)kh * (512u >> 4), w1_hi32),
+                               idesc1_lo, 1u);
+            }
+          }
+        }
+        __syncwarp();
+        if (ptx::elect_one()) {
+          ptx::tc_commit2(&bars->op_empty);
+          ptx::tc_commit2(&bars->acc1_full);
+        }
+        __syncwarp();
+      };
+      mma1(0);
+      for (long long step = 0; step < nsteps; ++step) {
+        if (step + 1 < nsteps) mma1(step + 1);
+        const uint32_t b = (uint32_t)(step & 1);
+        ptx::mbar_wait(&bars->acc2_empty[b], (uint32_t)((step >> 1) & 1) ^ 1u);
+        ptx::mbar_wait(&bars->reg_full, (uint32_t)(step & 1));
+        ptx::tc_fence_after();
+        if (!(TIC_DBG_BITS(p2.dbg) & 1) && ptx::elect_one()) {
+          const uint32_t d = tmem_base + 256u + b * 64u;
+          uint32_t sp = 0, fresh = 1;
+          u16_issue_plane_t<U16_S2, true, 2>(p2, reg_d, w2A_d, d, 2u * NPAD2, idesc2_st, a2_hi32, w2_hi32, tap2A >> 4, 0u, sp, fresh, true);
+          fresh = 0;
+          u16_issue_plane_t<U16_S2, true, 2>(p2, reg_d + (kFERegionPlane >> 4), w2B_d, d + (uint32_t)NPAD2, 2u * NPAD2, idesc2_lo, a2_hi32,
+                                             w2_hi32, tap2B >> 4, 0u, sp, fresh, false);
+        }
+        __syncwarp();
+        if (ptx::elect_one()) {
+          ptx::tc_commit2(&bars->reg_empty);
+          ptx::tc_commit2(&bars->acc2_full[b]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= kFEBuilderWarp0) {
+    // ===== builders: raw u8 window -> normalised (hi, lo') RGB0 quads of the 65 x 34-pixel input window =====
+    // item = (row, quad of 4 pixels): 65 x 9 = 585 items over 192 lanes; out-of-patch pixels (the conv's zero padding) are 0
+    const int bl = (warp - kFEBuilderWarp0) * 32 + lane;
+    const uint32_t* const plut0 = s_plut + (lane & (kFELutRep - 1));
+    const uint32_t* const plut1 = plut0 + 256 * kFELutRep;
+    const uint32_t* const plut2 = plut1 + 256 * kFELutRep;
+    long long step = 0;
+    for (long long pp = pair0; pp < fp.pairs_total; pp += npairs) {
+      for (int t = 0; t < fp.tiles_pp; ++t, ++step) {
+        int ty, tx;
+        tile_of(t, ty, tx);
+        const uint32_t r = (uint32_t)(step % kFERawStages);
+        ptx::mbar_wait(&bars->raw_full[r], (uint32_t)((step / kFERawStages) & 1));
+        ptx::mbar_wait(&bars->op_empty, (uint32_t)(step & 1) ^ 1u);   // MMA1 of the previous tile has read the operand buffer
+        const uint8_t* rawb = s_rawwin + (size_t)r * kFERawStage;
+        if (!(TIC_DBG_BITS(p2.dbg) & 8)) {
+#pragma unroll 1
+          for (int item = bl; item < kFEOpRows * 9; item += kFEBuilders * 32) {
+            const int ry = item / 9, qx = item - ry * 9;
+            const int iy = 64 * ty + ry, ix = 32 * tx + 4 * qx;
+            const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawb + (uint32_t)ry * kFERawRow + (uint32_t)qx * 12u);
+            const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
+            uint2 vh[4], vl[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
+              const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
+              const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
+              const bool okj = iy < fp.P && ix + j < fp.P;
+              const uint32_t x0 = okj ? plut0[b0 * kFELutRep] : 0u;
+              const uint32_t x1 = okj ? plut1[b1 * kFELutRep] : 0u;
+              const uint32_t x2 = okj ? plut2[b2 * kFELutRep] : 0u;
+              vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
+              vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
+            }
+            uint8_t* st = s_op + (uint32_t)ry * kFEOpPitch + (uint32_t)(4 * qx) * 8u;
+            const int npx = qx == 8 ? 2 : 4;   // the window is 34 pixels wide
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < npx) {
+                *reinterpret_cast<uint2*>(st + j * 8) = vh[j];
+                *reinterpret_cast<uint2*>(st + kFEOpPlane + j * 8) = vl[j];
+              }
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive(&bars->raw_empty[r]);
+          ptx::mbar_arrive_leader(&bars->op_full);
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < kFEBuilderWarp0) {
+    // ===== epilogue warps.  Per tile: A  first-layer accumulators -> registers, bias, relu, fp16 split (overlaps the
+    // previous tile's MMA2);  B  halo + region writes, "region full";  C  epilogue 2 of the previous tile. =====
+    const int q4 = warp & 3, sub = (warp - 4) >> 2;     // TMEM lane quadrant; first-layer sub-tile of this warp
+    const int m = q4 * 32 + lane, hh = m >> 3, xx = m & 7;
+    const int e = tid - 128;                            // 0 .. 511 among the epilogue threads
+    const uint32_t reg_hi = ptx::smem_u32(s_region), reg_lo = reg_hi + kFERegionPlane;
+    const uint32_t rowc = ptx::smem_u32(s_rowc), colc = ptx::smem_u32(s_colc);
+    const uint32_t rowc_par = (uint32_t)fp.tiles_x * 16u * 128u;
+    const uint32_t tq = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t tbuf1 = tq + (uint32_t)sub * 64u;
+    const float floor1 = a1.act ? 0.0f : -INFINITY;
+    const int R = (sub >> 1) * 16 + hh, C = (sub & 1) * 8 + xx;   // region coordinates of this lane's intermediate pixel
+    // byte offset of intermediate pixel (r, c) inside a region plane: the stride-2 box layout [h2][h parity][w2][w parity][32 ch]
+    auto cell = [](int r, int c) { return (uint32_t)((((r >> 1) * 2 + (r & 1)) * 9 + (c >> 1)) * 128 + (c & 1) * 64); };
+    const uint32_t pix = cell(R, C);
+    __half2 omax = __floats2half2_rn(0.f, 0.f);
+    int h_ones = 0, h_valid = 0;
+    // epilogue 2 (one warp per TMEM lane quadrant: the warps of sub-tile 0): the first layer's TMA-store epilogue
+    // (tic_first16.cuh) on encode_1's accumulators — 32 pixels x 32 channels, both planes staged, two bulk tensor stores
+    const bool e2_warp = sub == 0;
+    const uint32_t stage2 = ptx::smem_u32(s_stage + (size_t)q4 * kFEStagePerWarp);
+    auto epilogue2 = [&](long long estep, long long en, int ety, int etx) {
+      const uint32_t b = (uint32_t)(estep & 1);
+      ptx::mbar_wait(&bars->acc2_full[b], (uint32_t)((estep >> 1) & 1));
+      ptx::tc_fence_after();
+      if (!(TIC_DBG_BITS(p2.dbg) & 2)) {
+        f16_t2_epilogue_tile<32>(a2, &tm_ohi, &tm_olo, tq + 256u + b * 64u, NPAD2, (int)en, ety * 16 + 4 * q4, etx * 8, s_bias2, stage2, lane,
+                                 &bars->acc2_empty[b], omax, /*rel_leader=*/true, /*store=*/en < fp.n);
+      } else {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(&bars->acc2_empty[b]);
+      }
+    };
+    long long step = 0, pn = 0;
+    int pty = 0, ptx_ = 0;
+    for (long long pp = pair0; pp < fp.pairs_total; pp += npairs) {
+      for (int t = 0; t < fp.tiles_pp; ++t, ++step) {
+        int ty, tx;
+        tile_of(t, ty, tx);
+        // caches: this tile READS the row cache the tile below wrote (parity (ty + 1) & 1) and the column cache of the tile
+        // to the right (parity (tx + 1) & 1), and WRITES parities ty & 1 / tx & 1
+        const uint32_t rowc_rd = rowc + (uint32_t)((ty + 1) & 1) * rowc_par, rowc_wr = rowc + (uint32_t)(ty & 1) * rowc_par;
+        const uint32_t colc_rd = colc + (uint32_t)((tx + 1) & 1) * 4096u, colc_wr = colc + (uint32_t)(tx & 1) * 4096u;
+        const bool has_below = ty + 1 < fp.tiles_y, has_right = tx + 1 < fp.tiles_x;
+        // ---- phase A ----
+        ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1));
+        ptx::tc_fence_after();
+        uint32_t hp[2][8], lp[2][8];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          float v[16], u[16];
+          ptx::tmem_ld16_nowait(tbuf1 + (uint32_t)(32 + ci * 16), u);
+          ptx::tmem_ld16_nowait(tbuf1 + (uint32_t)(ci * 16), v);
+          ptx::tmem_ld_wait();
+          if (ci == 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_leader(&bars->acc1_empty);
+          }
+          const float4* bp = reinterpret_cast<const float4*>(s_bias1 + ci * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b = bp[i];
+            v[4 * i] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i], 1.0f / 2048.0f, v[4 * i]), b.x), floor1);
+            v[4 * i + 1] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 1], 1.0f / 2048.0f, v[4 * i + 1]), b.y), floor1);
+            v[4 * i + 2] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 2], 1.0f / 2048.0f, v[4 * i + 2]), b.z), floor1);
+            v[4 * i + 3] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 3], 1.0f / 2048.0f, v[4 * i + 3]), b.w), floor1);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[ci][i], lp[ci][i], omax);
+        }
+        // ---- phase B ----
+        ptx::mbar_wait(&bars->reg_empty, (uint32_t)(step & 1) ^ 1u);
+        asm volatile("bar.sync 2, 512;" ::: "memory");   // the previous tile's cache writes are visible
+        // halo: row 32 (17 pixels, corner last) and column 16 (32 pixels) of the region, 8 chunks of 16 B each
+        if (e < 49 * 8 && !(TIC_DBG_BITS(p2.dbg) & 4)) {
+          const int hx = e >> 3, ch = e & 7;              // ch 0..3: hi plane, 4..7: lo' plane
+          uint4 val = make_uint4(0u, 0u, 0u, 0u);
+          uint32_t dst;
+          if (hx < 17) {                                  // region row 32, column hx (corner hx = 16: the tile below-right)
+            if (has_below && (hx < 16 || has_right)) val = lds128(rowc_rd + (uint32_t)((tx * 16 + hx) * 128 + ch * 16));
+            dst = cell(32, hx);
+          } else {                                        // region column 16, row hx - 17
+            if (has_right) val = lds128(colc_rd + (uint32_t)((hx - 17) * 128 + ch * 16));
+            dst = cell(hx - 17, 16);
+          }
+          const uint32_t addr = (ch < 4 ? reg_hi : reg_lo) + dst + (uint32_t)(ch & 3) * 16u;
+          sts128(fused_swz128(addr), val.x, val.y, val.z, val.w);
+        }
+#pragma unroll
+        for (int ci = 0; ci < ((TIC_DBG_BITS(p2.dbg) & 4) ? 0 : 2); ++ci) {
+          const uint32_t ah = reg_hi + pix + (uint32_t)ci * 32u, al = reg_lo + pix + (uint32_t)ci * 32u;
+          sts128(fused_swz128(ah), hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
+          sts128(fused_swz128(ah + 16u), hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+          sts128(fused_swz128(al), lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+          sts128(fused_swz128(al + 16u), lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+          if (R == 0) {    // first row of the region: halo row of the tile above (corner of the tile above-left)
+            const uint32_t c0 = rowc_wr + (uint32_t)((tx * 16 + C) * 128 + ci * 32);
+            sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
+            sts128(c0 + 16u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+            sts128(c0 + 64u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+            sts128(c0 + 80u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+          }
+          if (C == 0) {    // first column: halo column of the tile to the left
+            const uint32_t c0 = colc_wr + (uint32_t)(R * 128 + ci * 32);
+            sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
+            sts128(c0 + 16u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+            sts128(c0 + 64u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+            sts128(c0 + 80u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(&bars->reg_full);
+        // ---- phase C: epilogue 2 of the previous tile ----
+        if (e2_warp && step > 0) epilogue2(step - 1, pn, pty, ptx_);
+        pn = 2 * pp + rank;
+        pty = ty;
+        ptx_ = tx;
+      }
+    }
+    if (e2_warp && step > 0) epilogue2(step - 1, pn, pty, ptx_);
+    if (e2_warp && lane == 0) ptx::bulk_wait_group<0>();   // every TMA store of this warp is complete before the CTA may exit
+    if (ovf_hit(omax)) ovf_raise(a1.oflow);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+// Which layer pairs take the fused kernel: the u8 image through conv 3 -> 32 stride 2 (TMA-fed windowed first layer)
+// followed by conv 32 -> 32 stride 2 into pair planes.
+inline bool fused_enc_supported(const LayerArgs& a1, int kind1, int stride1, const LayerArgs& a2, int kind2, int stride2) {
+  if (kind1 != 0 || kind2 != 0 || stride1 != 2 || stride2 != 2) return false;
+  if (a1.in_mode != IO_U8_NORM || a1.cin != 3 || a1.cout != 32 || a2.cin != 32 || a2.cout != 32) return false;
+  if (a1.res || a2.res || a2.out_mode != IO_ACT16) return false;
+  if (a1.hin != a1.win || a1.hin % 64 != 0 || a1.hin / 32 > kFusedMaxTilesX) return false;
+  if (a1.hout * 2 != a1.hin || a2.hin != a1.hout || a2.hout * 2 != a2.hin || a2.wout * 2 != a2.win) return false;
+  return f16_first_tma_ok(a1);
+}
+
+struct FusedEncWeights {
+  uint8_t* w1 = nullptr;
+  U16WeightSlice w2;
+  void release() {
+    if (w1) cudaFree(w1);
+    w1 = nullptr;
+    w2.release();
+  }
+};
+
+inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const LayerArgs& a2, const float* w1_dev, const float* w2_dev,
+                            FusedEncWeights* fw, int num_sms, std::string* err, int* launches) {
+  auto fail = [&](const std::string& what, int code) {
+    if (err) *err = what;
+    return code;
+  };
+  auto encode = umma_encode_fn();
+  if (!encode) return fail("cuTensorMapEncodeTiled is unavailable (driver too old?)", -2);
+  if (num_sms < 2) return fail("the fused encoder kernel needs CTA pairs", -5);
+  U16Plan pl2{};
+  if (!u16_plan(a2, 0, 2, a2.cout, &pl2, true)) return fail("fused encoder plan failed", -5);
+  U16Params p2 = pl2.p;
+  if (p2.mode != U16_S2 || p2.nbox != 1 || p2.ksteps != 2 || p2.KB != 1 || p2.bn != 1 || p2.npad != 32 || p2.nsplit != 1)
+    return fail("fused encoder: unexpected layer plan", -5);
+  if (!fw->w1) {
+    if (cudaMalloc(&fw->w1, 2 * 4608) != cudaSuccess) return fail("cudaMalloc for the fused first-layer weight image failed", -4);
+    f16_build_weights_s2_pair_kernel<<<8, 256, 0, stream>>>(w1_dev, a1.cout, fw->w1);
+    if (cudaGetLastError() != cudaSuccess) return fail("fused first-layer weight image kernel failed", -2);
+  }
+  if (u16_ensure_pair_weights(stream, w2_dev, a2, p2, &fw->w2) != 0) return fail("fused encoder: weight images failed", -2);
+  p2.wimg = fw->w2.img;
+  p2.dbg = tic_env_int("TIC_DBG", 0);  // -DTIC_ABLATE builds only: 1 no MMA2, 16 no MMA1, 2 no epilogue 2, 4 no region writes, 8 no builders
+
+  FusedEncParams fp{};
+  fp.n = a1.n;
+  fp.P = a1.hin;
+  fp.tiles_x = a2.wout / 8;
+  fp.tiles_y = a2.hout / 16;
+  fp.tiles_pp = fp.tiles_x * fp.tiles_y;
+  fp.pairs_total = ((long long)a1.n + 1) / 2;
+  fp.w1img = fw->w1;
+  auto up = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  uint32_t off = 0;
+  fp.w1_off = off;
+  off += up(4608);
+  fp.w2_off = off;
+  off += up(p2.wA_bytes);
+  fp.w2B_off = off;
+  off += up(p2.wB_bytes);
+  fp.op_off = off;
+  off += up(2u * kFEOpPlane);
+  fp.raw_off = off;
+  off += up(kFERawStages * kFERawStage);
+  fp.region_off = off;
+  off += 2u * kFERegionPlane;
+  fp.rowc_off = off;
+  off += 2u * (uint32_t)fp.tiles_x * 16u * 128u;
+  fp.colc_off = off;
+  off += 2u * 32u * 128u;
+  fp.stage_off = off;
+  off += 4u * kFEStagePerWarp;
+  fp.bars_off = off;
+  off += (uint32_t)sizeof(FusedEncBars);
+  fp.smem_bytes = off + 1024u;
+  if (fp.smem_bytes + 13312u /* static: table, biases */ > 227u * 1024u) return fail("fused encoder: shared memory plan does not fit", -5);
+
+  // raw image windows: 3-D map over [B, H, W * 3] bytes, box 65 rows x 112 bytes
+  CUtensorMap tm_img, tm_o[2];
+  {
+    const Geo& g = a1.geo;
+    const long long per_img = (long long)g.gh * g.gw;
+    const cuuint64_t nimg = (cuuint64_t)((g.n0 + a1.n + per_img - 1) / per_img);
+    cuuint64_t dims[3] = {(cuuint64_t)g.W * 3, (cuuint64_t)g.H, nimg};
+    cuuint64_t strides[2] = {(cuuint64_t)g.W * 3, (cuuint64_t)g.H * g.W * 3};
+    cuuint32_t box[3] = {kFERawRow, (cuuint32_t)kFEOpRows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode(&tm_img, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(a1.in), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (image windows) failed (" + std::to_string((int)r) + ")", -2);
+  }
+  {  // encode_1's output planes: box = one epilogue warp's 4 rows x 8 columns x 32 channels
+    const cuuint64_t C = a2.cout, Wd = a2.wout, Hd = a2.hout, Nd = a2.n;
+    cuuint64_t dims[4] = {C, Wd, Hd, Nd};
+    cuuint64_t strides[3] = {C * 2, Wd * C * 2, Hd * Wd * C * 2};
+    cuuint32_t box[4] = {32, 8, 4, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    for (int pl = 0; pl < 2; ++pl) {
+      void* base = reinterpret_cast<__half*>(a2.out) + (pl ? a2.out_lo_off : 0);
+      CUresult r = encode(&tm_o[pl], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (fused encoder output) failed (" + std::to_string((int)r) + ")", -2);
+    }
+  }
+  static SmemAttrCache cache;
+  if (cache.ensure(reinterpret_cast<const void*>(fused_enc_kernel), fp.smem_bytes) != cudaSuccess)
+    return fail("cudaFuncSetAttribute(fused encoder) failed", -2);
+  const int grid = 2 * (int)std::min<long long>(fp.pairs_total, num_sms / 2);
+  fused_enc_kernel<<<grid, kFEThreads, fp.smem_bytes, stream>>>(tm_img, tm_o[0], tm_o[1], a1, p2, a2, fp);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(std::string("fused encoder launch failed: ") + cudaGetErrorString(e), -2);
+  if (launches) ++*launches;
+  return 0;
+}
+
+}  // namespace tic

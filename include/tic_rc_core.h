@@ -21,8 +21,17 @@
  *     (A dyadic source that ends on a byte boundary therefore costs exactly its entropy: the reference's
  *     known-answer vector is 17 bytes of 0x0b.)
  *   - Several encode() calls with different tables may share one stream (the state just carries on).
+ *   - SEGMENTED CALLS.  A range coder is a serial recurrence: one image of BASELINE config 2 is 786 432 symbols, and 64
+ *     such streams keep neither 32 host threads nor a GPU busy.  So an encode() call of MORE than TIC_RC_SEGMENT_SYMBOLS
+ *     symbols made on a fresh stream (nothing coded yet, or right after another segmented call) is written as a
+ *     container: nseg = ceil(n / TIC_RC_SEGMENT_SYMBOLS) little-endian uint32 byte counts, then nseg independent streams
+ *     (each coded from the initial state, terminated and zero-stripped as above) of TIC_RC_SEGMENT_SYMBOLS symbols each
+ *     (the last one shorter).  After it the stream is fresh again.  The decoder applies the same rule to its decode(n)
+ *     calls, so nothing is stored beyond the byte counts.  Calls of at most TIC_RC_SEGMENT_SYMBOLS symbols (every test of
+ *     the reference's range_coder suite, including its known-answer vector) are plain streams.  Overhead: 4 bytes and one
+ *     termination (<= 5 bytes) per 32 768 symbols.
  * The range recurrence does not depend on low, and a binary symbol costs one shift, one multiply and one compare on
- * the critical path — what makes one-thread-per-stream viable on the GPU.
+ * the critical path; the segments are what both the host thread pool and the GPU stage parallelise over.
  */
 #ifndef TIC_RC_CORE_H_
 #define TIC_RC_CORE_H_
@@ -38,9 +47,19 @@
 #define TIC_RC_TOP (1u << 24)          /* renormalise below this */
 #define TIC_RC_MAX_TOTAL (1u << 16)    /* largest frequency total: r = range / total stays >= 256 */
 
-/* Worst-case stored bytes of a stream of n symbols (every symbol at the smallest width of the largest total costs
- * 16.006 bits) plus the flush. */
-static inline int64_t tic_rc_bound(int64_t n) { return 2 * n + (n >> 6) + 16; }
+#define TIC_RC_SEGMENT_SYMBOLS 32768    /* calls longer than this on a fresh stream are coded as independent segments */
+
+/* Worst-case stored bytes of a plain stream of n symbols (every symbol at the smallest width of the largest total costs
+ * 16.006 bits) plus the flush ... */
+TIC_RC_HD int64_t tic_rc_plain_bound(int64_t n) { return 2 * n + (n >> 6) + 16; }
+TIC_RC_HD int64_t tic_rc_segments(int64_t n) {
+  return n > TIC_RC_SEGMENT_SYMBOLS ? (n + TIC_RC_SEGMENT_SYMBOLS - 1) / TIC_RC_SEGMENT_SYMBOLS : 0;
+}
+/* ... and of what one encode() call of n symbols on a fresh stream writes (container header included) */
+TIC_RC_HD int64_t tic_rc_bound(int64_t n) {
+  const int64_t nseg = tic_rc_segments(n);
+  return nseg ? nseg * (4 + tic_rc_plain_bound(TIC_RC_SEGMENT_SYMBOLS)) : tic_rc_plain_bound(n);
+}
 
 typedef struct tic_rc_enc_state {
   uint64_t low;
@@ -102,12 +121,9 @@ template <class Sink>
 TIC_RC_HD void tic_rc_enc_bit(tic_rc_enc_state* s, Sink& out, uint32_t bit, int k, uint32_t c1) {
   const uint32_t r = s->range >> k;
   const uint32_t t = r * c1;
-  if (bit) {
-    s->low += t;
-    s->range = (r << k) - t;
-  } else {
-    s->range = t;
-  }
+  const uint32_t m = 0u - bit;   /* branch-free select: the symbols are close to coin flips */
+  s->low += (uint64_t)(t & m);
+  s->range = (t & ~m) | (((r << k) - t) & m);
   while (s->range < TIC_RC_TOP) {
     tic_rc_shift_low(s, out);
     s->range <<= 8;

@@ -133,10 +133,12 @@ def _host_streams(sym2d, cum):
     return range_coder.encode_streams(sym2d, cum, threads=0)
 
 
-@pytest.mark.parametrize("case", ["binary_pow2", "binary_skewed", "binary_total_3000", "q16", "q256_unaligned"])
+@pytest.mark.parametrize("case", ["binary_pow2", "binary_skewed", "binary_total_3000", "q16", "q256_unaligned", "segmented_ragged",
+                                  "segmented_q16"])
 def test_entropy_stage_is_byte_identical_to_the_host_coder(case):
     codec, _, _ = make_codec("model_0", "fanin")
-    rs = np.random.RandomState({"binary_pow2": 1, "binary_skewed": 2, "binary_total_3000": 3, "q16": 4, "q256_unaligned": 5}[case])
+    rs = np.random.RandomState({"binary_pow2": 1, "binary_skewed": 2, "binary_total_3000": 3, "q16": 4, "q256_unaligned": 5,
+                                "segmented_ragged": 6, "segmented_q16": 7}[case])
     if case == "binary_pow2":
         sym = (rs.rand(7, 24576) < 0.45).astype(np.uint8)
         cum = entry.cum_freq_table(np.bincount(sym.reshape(-1), minlength=2) / sym.size, 4096)
@@ -149,6 +151,13 @@ def test_entropy_stage_is_byte_identical_to_the_host_coder(case):
     elif case == "q16":
         p = rs.dirichlet([0.5] * 16)
         sym = rs.choice(16, size=(4, 8192), p=p).astype(np.uint8)
+        cum = range_coder.prob_to_cum_freq(p, resolution=1024)
+    elif case == "segmented_ragged":  # container format (include/tic_rc_core.h); odd length: unaligned streams, short last segment
+        sym = (rs.rand(3, 2 * 32768 + 4099) < 0.45).astype(np.uint8)
+        cum = [0, 2252, 4096]
+    elif case == "segmented_q16":
+        p = rs.dirichlet([0.5] * 16)
+        sym = rs.choice(16, size=(2, 3 * 32768), p=p).astype(np.uint8)
         cum = range_coder.prob_to_cum_freq(p, resolution=1024)
     else:
         p = rs.dirichlet([0.3] * 256)
@@ -185,6 +194,17 @@ def test_entropy_stage_errors():
         codec.entropy_encode(sym[:1], [1, 10, 16])
     out, nb = codec.entropy_encode(sym[:1], [0, 10, 16])
     assert int(nb[0]) <= out.shape[1]
+    # corrupt streams (plain and segmented) stay in bounds and decode to what the host decoder makes of the same bytes
+    rs = np.random.RandomState(8)
+    for n in (4096, 2 * 32768 + 5):
+        slot = int(codec.entropy_bound(n))
+        buf = np.zeros((2, slot), np.uint8)
+        nbytes = np.array([5000, 37], np.int64)
+        for i in range(2):
+            buf[i, :nbytes[i]] = rs.randint(0, 256, size=nbytes[i])
+        got = codec.entropy_decode(buf, nbytes, n, [0, 2252, 4096])
+        want = range_coder.decode_streams([bytes(buf[i, :nbytes[i]]) for i in range(2)], [n, n], [0, 2252, 4096])
+        assert all(np.array_equal(g, w) for g, w in zip(got, want)), n
     codec.close()
 
 

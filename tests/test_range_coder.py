@@ -146,6 +146,64 @@ def test_carry_propagation_and_stream_tail(tmp_path):
     e.close()
 
 
+def test_segmented_calls(tmp_path):
+    """include/tic_rc_core.h "SEGMENTED CALLS": a call of more than 32768 symbols on a fresh stream is a container of
+    little-endian uint32 byte counts followed by independently coded 32768-symbol streams; shorter calls, and calls on a
+    stream that already holds a plain call, are plain streams.  The decoder applies the same rule."""
+    SEG = 32768
+    rs = np.random.RandomState(21)
+    lib = RC.load()
+    for cum in ([0, 2252, 4096], [0, 700, 1000], [0, 10, 300, 301, 4096]):
+        k = len(cum) - 1
+        w = np.diff(cum) / cum[-1]
+        for n in (SEG, SEG + 1, 2 * SEG, 3 * SEG + 17):
+            s = rs.choice(k, size=n, p=w).astype(np.uint8)
+            blob, = RC.encode_streams([s], cum, threads=2)
+            assert len(blob) <= lib.tic_rc_max_encoded_bytes(n)
+            nseg = -(-n // SEG) if n > SEG else 0
+            if nseg == 0:
+                plain = blob
+            else:
+                lens = np.frombuffer(blob[:4 * nseg], "<u4")
+                assert 4 * nseg + int(lens.sum()) == len(blob)
+                at = 4 * nseg
+                for j, ln in enumerate(lens):
+                    piece = s[j * SEG:(j + 1) * SEG]
+                    assert blob[at:at + ln] == RC.encode_streams([piece], cum)[0]  # a plain stream of its own
+                    at += int(ln)
+            assert np.array_equal(RC.decode_streams([blob], [n], cum, threads=3)[0], s)
+            path = tmp_path / "seg.bin"
+            e = RC.RangeEncoder(str(path))
+            e.encode(s, cum)
+            e.close()
+            assert path.read_bytes() == blob
+    # several calls on one stream: segmented calls leave it fresh, the first plain call ends that
+    cum = [0, 2252, 4096]
+    calls = [(rs.rand(n) < 0.45).astype(np.uint8) for n in (2 * SEG + 5, SEG + 1, 100, SEG + 9, 7)]
+    path = tmp_path / "mixed.bin"
+    e = RC.RangeEncoder(str(path))
+    for c in calls:
+        e.encode(c, cum)
+    e.close()
+    raw = path.read_bytes()
+    first = RC.encode_streams([calls[0]], cum)[0] + RC.encode_streams([calls[1]], cum)[0]
+    assert raw[:len(first)] == first
+    # ... and what follows is ONE plain stream of the remaining three calls
+    rest = path.with_suffix(".rest")
+    e = RC.RangeEncoder(str(rest))
+    e.encode(np.concatenate(calls[2:])[:SEG], cum)       # (kept below the segment size: a plain call)
+    e.encode(np.concatenate(calls[2:])[SEG:], cum)
+    e.close()
+    assert raw[len(first):] == rest.read_bytes()
+    d = RC.RangeDecoder(str(path))
+    for c in calls:
+        assert np.array_equal(d.decode(len(c), cum, dtype=np.uint8), c)
+    d.close()
+    # a corrupt header cannot drive the decoder out of bounds: garbage decodes to garbage of the right length
+    bad = b"\xff" * 64
+    assert len(RC.decode_streams([bad], [SEG + 1], cum)[0]) == SEG + 1
+
+
 def test_rangecoder_library_exports_every_declared_symbol():
     import ctypes
     import re

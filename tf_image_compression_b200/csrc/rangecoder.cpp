@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <thread>
 #include <vector>
 
@@ -58,6 +59,10 @@ struct FileSink {
     }
     buf.clear();
   }
+  void put_raw(const uint8_t* src, size_t cnt) {
+    for (; zrun > 0; --zrun) raw(0);  // (a container only ever follows a fresh state: nothing is pending)
+    for (size_t i = 0; i < cnt; ++i) raw(src[i]);
+  }
 };
 
 // Sink into caller memory; `len` ends after the last non-zero byte (bytes are written as they come, so zeros inside
@@ -75,6 +80,16 @@ struct MemSink {
     p[pos++] = b;
     if (b) len = pos;
   }
+  // container bytes: stored as they are (a container is never zero-stripped; what follows it starts a fresh stream)
+  void put_raw(const uint8_t* src, size_t cnt) {
+    if (pos + (int64_t)cnt > cap) {
+      overflow = true;
+      return;
+    }
+    memcpy(p + pos, src, cnt);
+    pos += (int64_t)cnt;
+    len = pos;
+  }
 };
 
 struct FileSource {
@@ -91,6 +106,10 @@ struct FileSource {
     }
     return buf[pos++];
   }
+  // n raw bytes (container header / segment bodies); short reads are zero-filled like reads past EOF
+  void read_raw(uint8_t* dst, size_t n) {
+    for (size_t i = 0; i < n; ++i) dst[i] = (uint8_t)get();
+  }
 };
 
 struct MemSource {
@@ -98,6 +117,9 @@ struct MemSource {
   int64_t n, pos = 0;
   MemSource(const uint8_t* p_, int64_t n_) : p(p_), n(n_) {}
   uint32_t get() { return pos < n ? p[pos++] : 0u; }
+  void read_raw(uint8_t* dst, size_t cnt) {
+    for (size_t i = 0; i < cnt; ++i) dst[i] = (uint8_t)get();
+  }
 };
 
 template <typename T, class Sink>
@@ -136,6 +158,25 @@ int decode_symbols(tic_rc_dec_state* st, Source& in, T* out, int64_t n, const ui
   if (n_cum == 3) {
     // binary alphabet (every shipped config: quan_scale = 2): one compare instead of the division and the search
     const uint32_t c1 = cum[1];
+    if (p2 && c1 != 0 && c1 != total) {
+      // the shipped case, branch-free on the (near coin-flip) symbol value; same arithmetic as the loop below
+      uint32_t range = st->range, code = st->code;
+      for (int64_t i = 0; i < n; ++i) {
+        const uint32_t r = range >> k;
+        const uint32_t t = r * c1;
+        const uint32_t m = 0u - (uint32_t)(code >= t);
+        out[i] = (T)(m & 1u);
+        code -= t & m;
+        range = (t & ~m) | (((r << k) - t) & m);
+        while (range < TIC_RC_TOP) {
+          code = (code << 8) | in.get();
+          range <<= 8;
+        }
+      }
+      st->range = range;
+      st->code = code;
+      return TIC_RC_OK;
+    }
     for (int64_t i = 0; i < n; ++i) {
       const uint32_t r = p2 ? st->range >> k : st->range / total;
       const uint32_t t = r * c1;
@@ -180,16 +221,110 @@ void parallel_for(int64_t n, int n_threads, Fn fn) {
   for (auto& th : pool) th.join();
 }
 
+// ---- segmented calls (include/tic_rc_core.h): a call of more than TIC_RC_SEGMENT_SYMBOLS symbols on a fresh stream ----
+template <typename T>
+int encode_segment(const T* sym, int64_t n, const uint32_t* cum, int n_cum, std::vector<uint8_t>* out) {
+  // worst-case scratch once per worker thread (a fresh zero-filled 66 KB vector per segment cost more than the coding)
+  thread_local std::unique_ptr<uint8_t[]> scratch;
+  thread_local int64_t scratch_cap = 0;
+  const int64_t need = tic_rc_plain_bound(n);
+  if (scratch_cap < need) {
+    scratch.reset(new uint8_t[(size_t)need]);
+    scratch_cap = need;
+  }
+  tic_rc_enc_state st;
+  tic_rc_enc_init(&st);
+  MemSink sink(scratch.get(), need);
+  int rc = encode_symbols(&st, sink, sym, n, cum, n_cum);
+  if (rc != TIC_RC_OK) return rc;
+  tic_rc_enc_finish(&st, sink);
+  if (sink.overflow) return TIC_RC_ERR_IO;
+  out->assign(scratch.get(), scratch.get() + sink.len);
+  return TIC_RC_OK;
+}
+
+// header (nseg little-endian uint32 byte counts) + bodies into any sink with put_raw
+template <typename T, class Sink>
+int encode_segmented(Sink& out, const T* sym, int64_t n, const uint32_t* cum, int n_cum, int n_threads) {
+  const int64_t nseg = tic_rc_segments(n);
+  std::vector<std::vector<uint8_t>> body((size_t)nseg);
+  std::atomic<int> status{TIC_RC_OK};
+  parallel_for(nseg, n_threads, [&](int64_t j) {
+    const int64_t s0 = j * TIC_RC_SEGMENT_SYMBOLS, len = std::min<int64_t>(TIC_RC_SEGMENT_SYMBOLS, n - s0);
+    const int r = encode_segment(sym + s0, len, cum, n_cum, &body[(size_t)j]);
+    if (r != TIC_RC_OK) status.store(r);
+  });
+  if (status.load() != TIC_RC_OK) return status.load();
+  std::vector<uint8_t> hdr((size_t)nseg * 4);
+  for (int64_t j = 0; j < nseg; ++j) {
+    const uint32_t v = (uint32_t)body[(size_t)j].size();
+    hdr[4 * j] = (uint8_t)v;
+    hdr[4 * j + 1] = (uint8_t)(v >> 8);
+    hdr[4 * j + 2] = (uint8_t)(v >> 16);
+    hdr[4 * j + 3] = (uint8_t)(v >> 24);
+  }
+  out.put_raw(hdr.data(), hdr.size());
+  for (auto& b : body) out.put_raw(b.data(), b.size());
+  return TIC_RC_OK;
+}
+
+template <typename T, class Source>
+int decode_segmented(Source& in, T* out, int64_t n, const uint32_t* cum, int n_cum, int n_threads) {
+  const int64_t nseg = tic_rc_segments(n);
+  std::vector<uint8_t> hdr((size_t)nseg * 4);
+  in.read_raw(hdr.data(), hdr.size());
+  std::vector<std::vector<uint8_t>> body((size_t)nseg);
+  for (int64_t j = 0; j < nseg; ++j) {
+    uint32_t v = (uint32_t)hdr[4 * j] | ((uint32_t)hdr[4 * j + 1] << 8) | ((uint32_t)hdr[4 * j + 2] << 16) | ((uint32_t)hdr[4 * j + 3] << 24);
+    v = (uint32_t)std::min<int64_t>(v, tic_rc_plain_bound(TIC_RC_SEGMENT_SYMBOLS));  // corrupt header: stay bounded
+    body[(size_t)j].resize(v);
+    in.read_raw(body[(size_t)j].data(), v);
+  }
+  parallel_for(nseg, n_threads, [&](int64_t j) {
+    const int64_t s0 = j * TIC_RC_SEGMENT_SYMBOLS, len = std::min<int64_t>(TIC_RC_SEGMENT_SYMBOLS, n - s0);
+    tic_rc_dec_state st;
+    tic_rc_dec_init(&st);
+    MemSource src(body[(size_t)j].data(), (int64_t)body[(size_t)j].size());
+    decode_symbols(&st, src, out + s0, len, cum, n_cum);
+  });
+  return TIC_RC_OK;
+}
+
+// One encode() call: segmented when the stream is fresh and the call is long, plain otherwise.
+template <typename T, class Sink>
+int encode_call(tic_rc_enc_state* st, bool* fresh, Sink& out, const T* sym, int64_t n, const uint32_t* cum, int n_cum, int n_threads) {
+  if (*fresh && tic_rc_segments(n) > 0) {
+    // validate the symbols before anything is written (a failing call must not leave half a container behind)
+    const int64_t nsym = n_cum - 1;
+    for (int64_t i = 0; i < n; ++i) {
+      const int64_t s = (int64_t)sym[i];
+      if (s < 0 || s >= nsym || cum[s + 1] == cum[s]) return TIC_RC_ERR_SYMBOL;
+    }
+    return encode_segmented(out, sym, n, cum, n_cum, n_threads);  // the stream stays fresh
+  }
+  if (n > 0) *fresh = false;
+  return encode_symbols(st, out, sym, n, cum, n_cum);
+}
+
+template <typename T, class Source>
+int decode_call(tic_rc_dec_state* st, bool* fresh, Source& in, T* out, int64_t n, const uint32_t* cum, int n_cum, int n_threads) {
+  if (*fresh && tic_rc_segments(n) > 0) return decode_segmented(in, out, n, cum, n_cum, n_threads);
+  if (n > 0) *fresh = false;
+  return decode_symbols(st, in, out, n, cum, n_cum);
+}
+
 }  // namespace
 
 struct tic_rc_encoder {
   tic_rc_enc_state st;
   FileSink out;
+  bool fresh = true;
 };
 
 struct tic_rc_decoder {
   tic_rc_dec_state st;
   FileSource in;
+  bool fresh = true;
 };
 
 extern "C" {
@@ -211,7 +346,7 @@ int tic_rc_encode_u8(tic_rc_encoder* e, const uint8_t* symbols, int64_t n, const
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return encode_symbols(&e->st, e->out, symbols, n, cum_freq, n_cum);
+  return encode_call(&e->st, &e->fresh, e->out, symbols, n, cum_freq, n_cum, 0);
 }
 
 int tic_rc_encode_i32(tic_rc_encoder* e, const int32_t* symbols, int64_t n, const uint32_t* cum_freq, int n_cum) {
@@ -219,7 +354,7 @@ int tic_rc_encode_i32(tic_rc_encoder* e, const int32_t* symbols, int64_t n, cons
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return encode_symbols(&e->st, e->out, symbols, n, cum_freq, n_cum);
+  return encode_call(&e->st, &e->fresh, e->out, symbols, n, cum_freq, n_cum, 0);
 }
 
 int tic_rc_encoder_close(tic_rc_encoder* e) {
@@ -258,7 +393,7 @@ int tic_rc_decode_u8(tic_rc_decoder* d, uint8_t* symbols, int64_t n, const uint3
   if (rc != TIC_RC_OK) return rc;
   if (n_cum - 1 > 256) return TIC_RC_ERR_TABLE;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return decode_symbols(&d->st, d->in, symbols, n, cum_freq, n_cum);
+  return decode_call(&d->st, &d->fresh, d->in, symbols, n, cum_freq, n_cum, 0);
 }
 
 int tic_rc_decode_i32(tic_rc_decoder* d, int32_t* symbols, int64_t n, const uint32_t* cum_freq, int n_cum) {
@@ -266,7 +401,7 @@ int tic_rc_decode_i32(tic_rc_decoder* d, int32_t* symbols, int64_t n, const uint
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n > 0 && !symbols) return TIC_RC_ERR_SYMBOL;
-  return decode_symbols(&d->st, d->in, symbols, n, cum_freq, n_cum);
+  return decode_call(&d->st, &d->fresh, d->in, symbols, n, cum_freq, n_cum, 0);
 }
 
 int tic_rc_decoder_close(tic_rc_decoder* d) {
@@ -289,18 +424,47 @@ int tic_rc_encode_streams(const uint8_t* symbols, const int64_t* sym_offsets, in
   int rc = check_table(cum_freq, n_cum);
   if (rc != TIC_RC_OK) return rc;
   if (n_streams < 0 || (n_streams > 0 && (!symbols || !sym_offsets || !out || !out_offsets || !out_bytes))) return TIC_RC_ERR_SYMBOL;
-  std::atomic<int> status{TIC_RC_OK};
-  parallel_for(n_streams, n_threads, [&](int64_t i) {
-    tic_rc_enc_state st;
-    tic_rc_enc_init(&st);
-    MemSink sink(out + out_offsets[i], out_offsets[i + 1] - out_offsets[i]);
-    int r = encode_symbols(&st, sink, symbols + sym_offsets[i], sym_offsets[i + 1] - sym_offsets[i], cum_freq, n_cum);
-    if (r == TIC_RC_OK) {
-      tic_rc_enc_finish(&st, sink);
-      if (sink.overflow) r = TIC_RC_ERR_IO;
+  // work items: every segment of every long stream, every short stream as a whole — all on one thread pool
+  struct Item {
+    int64_t stream, seg, s0, len;
+  };
+  std::vector<Item> items;
+  std::vector<int64_t> first(n_streams + 1, 0);
+  for (int64_t i = 0; i < n_streams; ++i) {
+    const int64_t n = sym_offsets[i + 1] - sym_offsets[i], nseg = tic_rc_segments(n);
+    first[i] = (int64_t)items.size();
+    if (nseg == 0) {
+      items.push_back({i, -1, 0, n});
+    } else {
+      for (int64_t j = 0; j < nseg; ++j)
+        items.push_back({i, j, j * TIC_RC_SEGMENT_SYMBOLS, std::min<int64_t>(TIC_RC_SEGMENT_SYMBOLS, n - j * TIC_RC_SEGMENT_SYMBOLS)});
     }
-    out_bytes[i] = r == TIC_RC_OK ? sink.len : 0;
+  }
+  first[n_streams] = (int64_t)items.size();
+  std::vector<std::vector<uint8_t>> body(items.size());
+  std::atomic<int> status{TIC_RC_OK};
+  parallel_for((int64_t)items.size(), n_threads, [&](int64_t k) {
+    const Item& it = items[(size_t)k];
+    const int r = encode_segment(symbols + sym_offsets[it.stream] + it.s0, it.len, cum_freq, n_cum, &body[(size_t)k]);
     if (r != TIC_RC_OK) status.store(r);
+  });
+  if (status.load() != TIC_RC_OK) {
+    for (int64_t i = 0; i < n_streams; ++i) out_bytes[i] = 0;
+    return status.load();
+  }
+  parallel_for(n_streams, n_threads, [&](int64_t i) {
+    MemSink sink(out + out_offsets[i], out_offsets[i + 1] - out_offsets[i]);
+    const int64_t k0 = first[i], k1 = first[i + 1];
+    if (items[(size_t)k0].seg >= 0) {
+      for (int64_t k = k0; k < k1; ++k) {
+        const uint32_t v = (uint32_t)body[(size_t)k].size();
+        const uint8_t h4[4] = {(uint8_t)v, (uint8_t)(v >> 8), (uint8_t)(v >> 16), (uint8_t)(v >> 24)};
+        sink.put_raw(h4, 4);
+      }
+    }
+    for (int64_t k = k0; k < k1; ++k) sink.put_raw(body[(size_t)k].data(), body[(size_t)k].size());
+    out_bytes[i] = sink.overflow ? 0 : sink.pos;
+    if (sink.overflow) status.store(TIC_RC_ERR_IO);
   });
   return status.load();
 }
@@ -311,11 +475,38 @@ int tic_rc_decode_streams(const uint8_t* in, const int64_t* in_offsets, const in
   if (rc != TIC_RC_OK) return rc;
   if (n_cum - 1 > 256) return TIC_RC_ERR_TABLE;
   if (n_streams < 0 || (n_streams > 0 && (!in || !in_offsets || !in_bytes || !symbols || !sym_offsets))) return TIC_RC_ERR_SYMBOL;
-  parallel_for(n_streams, n_threads, [&](int64_t i) {
+  struct Item {
+    const uint8_t* p;
+    int64_t bytes;
+    uint8_t* out;
+    int64_t len;
+  };
+  std::vector<Item> items;
+  for (int64_t i = 0; i < n_streams; ++i) {
+    const int64_t n = sym_offsets[i + 1] - sym_offsets[i], nseg = tic_rc_segments(n);
+    const uint8_t* base = in + in_offsets[i];
+    const int64_t have = in_bytes[i];
+    if (nseg == 0) {
+      items.push_back({base, have, symbols + sym_offsets[i], n});
+      continue;
+    }
+    int64_t pos = 4 * nseg;
+    for (int64_t j = 0; j < nseg; ++j) {
+      uint32_t v = 0;
+      for (int b = 0; b < 4; ++b)
+        if (4 * j + b < have) v |= (uint32_t)base[4 * j + b] << (8 * b);
+      const int64_t avail = std::max<int64_t>(0, std::min<int64_t>(v, have - pos));  // corrupt header: stay inside the stream
+      items.push_back({base + std::min(pos, have), avail, symbols + sym_offsets[i] + j * TIC_RC_SEGMENT_SYMBOLS,
+                       std::min<int64_t>(TIC_RC_SEGMENT_SYMBOLS, n - j * TIC_RC_SEGMENT_SYMBOLS)});
+      pos += v;
+    }
+  }
+  parallel_for((int64_t)items.size(), n_threads, [&](int64_t k) {
+    const Item& it = items[(size_t)k];
     tic_rc_dec_state st;
     tic_rc_dec_init(&st);
-    MemSource src(in + in_offsets[i], in_bytes[i]);
-    decode_symbols(&st, src, symbols + sym_offsets[i], sym_offsets[i + 1] - sym_offsets[i], cum_freq, n_cum);
+    MemSource src(it.p, it.bytes);
+    decode_symbols(&st, src, it.out, it.len, cum_freq, n_cum);
   });
   return TIC_RC_OK;
 }

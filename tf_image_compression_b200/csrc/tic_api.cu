@@ -88,6 +88,9 @@ struct tic_codec {
                                     // [1] entropy stage (1: symbol outside the table / of zero width, 2: slot too small)
   unsigned int* d_oflow = nullptr;  // their device address
   uint32_t* d_cum = nullptr;        // entropy stage: the call's cumulative-frequency table [257]
+  uint8_t* d_seg = nullptr;         // entropy stage: worst-case slots of a segmented call's pieces (grow-only)
+  long long* d_seg_bytes = nullptr; //   and their stored lengths
+  int64_t seg_cap = 0;              //   pieces both hold
   cudaEvent_t ev_switch = nullptr;  // orders the old stream before the new one in tic_set_stream
   std::string err;
 };
@@ -897,6 +900,8 @@ void tic_destroy(tic_codec* h) {
   if (h->d_symlut) cudaFree(h->d_symlut);
   if (h->h_oflow) cudaFreeHost(h->h_oflow);
   if (h->d_cum) cudaFree(h->d_cum);
+  if (h->d_seg) cudaFree(h->d_seg);
+  if (h->d_seg_bytes) cudaFree(h->d_seg_bytes);
   if (h->ev_switch) cudaEventDestroy(h->ev_switch);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -1584,9 +1589,32 @@ int tic_entropy_encode(tic_codec* h, const uint8_t* symbols, int64_t n_streams, 
     dout = (uint8_t*)t_out;
     dbytes = (long long*)t_bytes;
   }
+  const int64_t nseg = tic_rc_segments(stream_len);
+  if (nseg > 0x7fffffffLL / std::max<int64_t>(1, n_streams)) return fail(h, TIC_ERR_INVALID, "too many segments");
+  if (nseg > 0 && n_streams * nseg > h->seg_cap) {
+    // grow-only scratch: the stream is drained first, earlier calls may still be packing out of the old buffer
+    TIC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_seg) cudaFree(h->d_seg);
+    if (h->d_seg_bytes) cudaFree(h->d_seg_bytes);
+    h->d_seg = nullptr;
+    h->d_seg_bytes = nullptr;
+    h->seg_cap = 0;
+    TIC_CUDA(h, cudaMalloc(&h->d_seg, (size_t)(n_streams * nseg * kEntropySegSlot)));
+    TIC_CUDA(h, cudaMalloc(&h->d_seg_bytes, (size_t)(n_streams * nseg) * sizeof(long long)));
+    h->seg_cap = n_streams * nseg;
+  }
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
-  rc_encode_kernel<<<(unsigned)n_streams, 32, 0, h->stream>>>(dsym, stream_len, h->d_cum, n_cum, dout, out_stride, dbytes, h->d_oflow + 1);
-  h->launches++;
+  if (nseg == 0) {
+    rc_encode_kernel<<<(unsigned)n_streams, 32, 0, h->stream>>>(dsym, stream_len, stream_len, 1, h->d_cum, n_cum, dout, out_stride, dbytes,
+                                                                  h->d_oflow + 1);
+    h->launches++;
+  } else {
+    rc_encode_kernel<<<(unsigned)(n_streams * nseg), 32, 0, h->stream>>>(dsym, stream_len, TIC_RC_SEGMENT_SYMBOLS, (int)nseg, h->d_cum, n_cum,
+                                                                           h->d_seg, kEntropySegSlot, h->d_seg_bytes, h->d_oflow + 1);
+    rc_pack_kernel<<<(unsigned)(n_streams * nseg), 256, 0, h->stream>>>(h->d_seg, h->d_seg_bytes, (int)nseg, dout, out_stride, dbytes,
+                                                                                      h->d_oflow + 1);
+    h->launches += 2;
+  }
   cudaError_t e = cudaGetLastError();
   cudaEventRecord(h->ev_t1, h->stream);
   if (mem == TIC_MEM_HOST) {
@@ -1643,7 +1671,10 @@ int tic_entropy_decode(tic_codec* h, const uint8_t* in, int64_t n_streams, int64
     return fail(h, TIC_ERR_INVALID, "entropy decode: the stream buffer must be 16-byte aligned");
   }
   TIC_CUDA(h, cudaEventRecord(h->ev_t0, h->stream));
-  rc_decode_kernel<<<(unsigned)n_streams, 32, 0, h->stream>>>(din, in_stride, dbytes, h->d_cum, n_cum, dsym, stream_len);
+  const int64_t nseg = tic_rc_segments(stream_len);
+  if (nseg > 0x7fffffffLL / n_streams) return fail(h, TIC_ERR_INVALID, "too many segments");
+  rc_decode_kernel<<<(unsigned)(n_streams * std::max<int64_t>(1, nseg)), 32, 0, h->stream>>>(din, in_stride, dbytes, h->d_cum, n_cum, dsym,
+                                                                                                stream_len, (int)nseg);
   h->launches++;
   cudaError_t e = cudaGetLastError();
   cudaEventRecord(h->ev_t1, h->stream);

@@ -80,6 +80,15 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in L.load().tic_version()
 
 
+def test_shipped_library_has_no_ablation_knobs():
+    """The stage-ablation / tuning environment knobs (TIC_DBG, TIC_FUSE_DEC, TIC_FUSE_ENC, TIC_MAX_NBUF, TIC_FIRST_NO_TMA ...)
+    exist only in builds with -DTIC_ABLATE (tools/build_lib.sh with TIC_EXTRA_FLAGS): the shipped library does not know their names,
+    so no such variable can change its results."""
+    blob = Path(L.LIB_PATH).read_bytes()   # (getenv itself is linked in by the static CUDA runtime)
+    for knob in (b"TIC_DBG", b"TIC_FUSE_DEC", b"TIC_FUSE_ENC", b"TIC_MAX_NBUF", b"TIC_FIRST_NO_TMA", b"TIC_L2_BUDGET_MB"):
+        assert knob not in blob, knob
+
+
 def test_no_gpu_fails_loudly_without_fallback():
     import torch
     if torch.cuda.is_available():

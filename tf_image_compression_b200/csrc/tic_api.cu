@@ -28,6 +28,7 @@ struct Layer {
   tic_layer_desc d{};
   float* w = nullptr;     // device [9][cin][cout]
   float* b = nullptr;     // device [cout]
+  std::vector<float> hb;  // host copy of the bias (the fused kernels take it as launch constants)
   UmmaWeights uw;         // tensor-path operand images (built lazily from w)
   U16Weights uw16;        // fp16-pair operand images
   F16Weights fw16;        // fp16-pair first-layer (cin = 3) operand image
@@ -573,7 +574,7 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
           a2.geo.n0 += s0;
           if (a2.out && fused_dec_supported(a, d.kind, a2, ly2.d.kind)) {
             int nl = 0;
-            rc = launch_fused_dec(h->stream, a, a2, ly.w, ly2.w, &ly.fdw, h->num_sms, &h->err, &nl);
+            rc = launch_fused_dec(h->stream, a, a2, ly.w, ly2.w, ly.hb.data(), ly2.hb.data(), &ly.fdw, h->num_sms, &h->err, &nl);
             h->launches += nl;
             fused = true;
           }
@@ -603,7 +604,7 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
           a2.out_lo_off = (long long)ns * t2.hout * t2.wout * t2.cout;
           if (fused_enc_supported(a, d.kind, d.stride, a2, ly2.d.kind, ly2.d.stride)) {
             int nl = 0;
-            rc = launch_fused_enc(h->stream, a, a2, ly.w, ly2.w, &ly.few, h->num_sms, &h->err, &nl);
+            rc = launch_fused_enc(h->stream, a, a2, ly.w, ly2.w, ly.hb.data(), &ly.few, h->num_sms, &h->err, &nl);
             h->launches += nl;
             fused = true;
             ob = 0;  // the pair's output lives in act[0]
@@ -1017,6 +1018,7 @@ int tic_load_weights(tic_codec* h, int graph, int layer, const float* kernel, co
   TIC_CUDA(h, cudaStreamSynchronize(h->stream));
   TIC_CUDA(h, cudaMemcpy(l.w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
   TIC_CUDA(h, cudaMemcpy(l.b, bias, (size_t)cout * sizeof(float), cudaMemcpyHostToDevice));
+  l.hb.assign(bias, bias + cout);
   l.uw.release();
   l.uw16.release();
   l.fw16.release();
@@ -1688,6 +1690,19 @@ int tic_entropy_decode(tic_codec* h, const uint8_t* in, int64_t n_streams, int64
   if (e != cudaSuccess) return fail(h, TIC_ERR_CUDA, "entropy decode failed: %s", cudaGetErrorString(e));
   return TIC_OK;
 }
+
+#ifdef TIC_ABLATE
+// ablation builds only (tools/fused_waits.py): the fused kernels' wait-time counters of cluster 0
+extern "C" int tic_debug_prof_read(unsigned long long* out64, int reset) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (out64 && cudaMemcpyFromSymbol(out64, g_tic_prof, sizeof(unsigned long long) * 64) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[64] = {};
+    if (cudaMemcpyToSymbol(g_tic_prof, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif
 
 int tic_check_status(tic_codec* h) {
   if (!h) return TIC_ERR_INVALID;

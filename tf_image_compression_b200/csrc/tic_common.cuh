@@ -14,6 +14,20 @@ namespace tic {
 // (tools/build_ablate.sh).  The shipped library ignores every TIC_* environment variable: a stray variable must
 // never change what a kernel computes.
 #ifdef TIC_ABLATE
+// wait-time accounting of the fused kernels' roles (cluster 0 only): cycles spent inside each barrier wait, summed over the
+// kernel's steps, read back by tools/fused_waits.py through tic_debug_prof_read (not part of the shipped ABI)
+__device__ unsigned long long g_tic_prof[64];
+#define TIC_PROF_WAIT(acc, ...)            \
+  do {                                     \
+    const long long _t0 = clock64();       \
+    __VA_ARGS__;                           \
+    (acc) += clock64() - _t0;              \
+  } while (0)
+#define TIC_PROF_NOW() clock64()
+#define TIC_PROF_ADD(slot, v)                                                                     \
+  do {                                                                                            \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) atomicAdd(&g_tic_prof[slot], (unsigned long long)(v)); \
+  } while (0)
 inline int tic_env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -21,6 +35,14 @@ inline int tic_env_int(const char* name, int dflt) {
 inline bool tic_env_set(const char* name) { return getenv(name) != nullptr; }
 #define TIC_DBG_BITS(x) (x)
 #else
+#define TIC_PROF_WAIT(acc, ...) \
+  do {                          \
+    __VA_ARGS__;                \
+  } while (0)
+#define TIC_PROF_NOW() 0LL
+#define TIC_PROF_ADD(slot, v) \
+  do {                        \
+  } while (0)
 inline int tic_env_int(const char*, int dflt) { return dflt; }
 inline bool tic_env_set(const char*) { return false; }
 #define TIC_DBG_BITS(x) 0

@@ -32,6 +32,11 @@ constexpr int kFusedThreads = 32 * (4 + kFusedEpiWarps);  // 640
 constexpr int kFusedRegionCols = 17, kFusedRegionRows = 33;
 constexpr uint32_t kFusedRegionPitch = kFusedRegionCols * 64;                 // bytes per region row and plane (32 ch fp16)
 constexpr uint32_t kFusedRegionPlane = 36864;                                   // >= 33 * 17 * 64 = 35904, multiple of 1024
+// The lo' plane starts one pixel (64 B) past a 128-byte line: a warp's 32 pixels of one output phase all have the same
+// pixel parity, so a 16-byte store per lane into ONE plane touches only four of the eight 16-byte bank groups (2-way
+// conflict, ncu: x2.4 the ideal wavefronts and the kernel sits on the shared-memory data pipe).  With the planes half a
+// line apart, half the lanes store their hi chunk while the other half store their lo' chunk: eight bank groups.
+constexpr uint32_t kFusedRegionLoOff = kFusedRegionPlane + 64;
 constexpr int kFusedMaxTilesX = 8;
 
 struct FusedDecParams {
@@ -41,6 +46,8 @@ struct FusedDecParams {
   long long pairs_total;    // ceil(n / 2)
   uint32_t w1_off, w1B_off, w2_off, w2B_off, in_off, region_off, rowc_off, colc_off, corner_off, bars_off;
   uint32_t smem_bytes;
+  float bias1[32];          // decode_1's bias as launch constants (constant-bank operands: no shared-memory loads in phase A)
+  float bias2[4];           // decode_0's
 };
 
 struct FusedDecBars {
@@ -53,6 +60,60 @@ struct FusedDecBars {
 };
 
 __device__ __forceinline__ uint32_t fused_swz64(uint32_t addr) { return addr ^ (((addr >> 7) & 3u) << 4); }
+
+// decode_0's epilogue for one lane of a 16 x 8 sub-tile: the 16 accumulator columns are (output phase (py, px), channel) of
+// the 2 x 2 image pixels of this lane's region pixel (yt, xt).  Bias, denormalise, clip (model_0/model.py:250-259), round
+// (decode.py:249), both output rows from ONE pair of TMEM loads and one patch -> image decode (the shared epilogue of
+// tic_umma16.cuh takes a row per call: twice the loads, twelve selects).
+__device__ __forceinline__ void fused_rgb_epilogue(const LayerArgs& a, const uint32_t tbuf, const int NPAD, const int n, const int yt,
+                                                   const int xt, const bool valid, const float* bias3) {
+  float v[16], u[16];
+  ptx::tmem_ld16_nowait(tbuf + NPAD, u);
+  ptx::tmem_ld16_nowait(tbuf, v);
+  ptx::tmem_ld_wait();
+  if (!valid) return;
+  const Geo& g = a.geo;
+  unsigned img, gy, gx;
+  geo_decode(g, (unsigned)(g.n0 + n), img, gy, gx);   // utils.concat_patches, utils/utils.py:136-167: crop to [H, W]
+  const int Y0 = g.oy + (int)gy * g.P + 2 * yt, X = g.ox + (int)gx * g.P + 2 * xt;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int Y = Y0 + half;
+    if (Y >= g.H) break;
+    const long long off = (((long long)img * g.H + Y) * g.W + X) * 3;
+    float y[6];
+#pragma unroll
+    for (int px = 0; px < 2; ++px)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int col = (half * 2 + px) * 4 + c;
+        const float t = apply_act(__fadd_rn(__fmaf_rn(u[col], 1.0f / 2048.0f, v[col]), bias3[c]), a.act);
+        y[px * 3 + c] = tic_denorm_clip(t, a.mean[c], a.stdv[c]);
+      }
+    if (a.out_mode == IO_DENORM_U8 && X + 1 < g.W && !(off & 1)) {
+      // both pixels inside the image and 2-byte aligned (X is even: any even W): three 2-byte stores
+      uint32_t q[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) q[i] = (uint32_t)(int)rintf(y[i]);
+      unsigned short* o2 = reinterpret_cast<unsigned short*>(reinterpret_cast<uint8_t*>(a.out) + off);
+      o2[0] = (unsigned short)(q[0] | (q[1] << 8));
+      o2[1] = (unsigned short)(q[2] | (q[3] << 8));
+      o2[2] = (unsigned short)(q[4] | (q[5] << 8));
+    } else {
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        if (X + px >= g.W) break;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (a.out_mode == IO_DENORM_F32)
+            reinterpret_cast<float*>(a.out)[off + px * 3 + c] = y[px * 3 + c];
+          else
+            reinterpret_cast<uint8_t*>(a.out)[off + px * 3 + c] = (uint8_t)(int)rintf(y[px * 3 + c]);
+        }
+      }
+    }
+  }
+}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
 fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const U16Params p1,
@@ -68,15 +129,11 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][tiles_x][16 px][hi 64 B | lo 64 B]
   uint8_t* s_colc = smem + fp.colc_off;        // [parity][32 px][hi | lo]
   FusedDecBars* bars = reinterpret_cast<FusedDecBars*>(smem + fp.bars_off);
-  __shared__ __align__(16) float s_bias1[32];
-  __shared__ __align__(16) float s_bias2[4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
 
-  if (tid < 32) s_bias1[tid] = tid < a1.cout ? a1.bias[tid] : 0.f;
-  if (tid < 4) s_bias2[tid] = tid < a2.cout ? a2.bias[tid] : 0.f;
   if (tid == 0) {
     ptx::mbar_init(&bars->w_full, leader ? 2 : 1);
     for (int i = 0; i < 2; ++i) {
@@ -159,10 +216,12 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const uint32_t w2A_d = (ptx::smem_u32(s_w2A) >> 4) | (1u << 16), w2B_d = (ptx::smem_u32(s_w2B) >> 4) | (1u << 16);
       const uint32_t reg_d = (ptx::smem_u32(s_region) >> 4) | (1u << 16);
       ptx::mbar_wait(&bars->w_full, 0);
+      long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
+      const long long pt0 = TIC_PROF_NOW();
       auto mma1 = [&](long long step) {
         const uint32_t s = (uint32_t)(step & 1);
-        ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u);
-        ptx::mbar_wait(&bars->in_full[s], (uint32_t)((step >> 1) & 1));
+        TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u));
+        TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->in_full[s], (uint32_t)((step >> 1) & 1)));
         ptx::tc_fence_after();
         if (!(TIC_DBG_BITS(p1.dbg) & 16) && ptx::elect_one()) {
           const uint32_t ah = (ptx::smem_u32(s_in + (size_t)s * slot_bytes) >> 4) | (1u << 16);
@@ -184,15 +243,15 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       for (long long step = 0; step < nsteps; ++step) {
         if (step + 1 < nsteps) mma1(step + 1);
         const uint32_t b = (uint32_t)(step & 1);
-        ptx::mbar_wait(&bars->acc2_empty[b], (uint32_t)((step >> 1) & 1) ^ 1u);
-        ptx::mbar_wait(&bars->reg_full, (uint32_t)(step & 1));
+        TIC_PROF_WAIT(pw2, ptx::mbar_wait(&bars->acc2_empty[b], (uint32_t)((step >> 1) & 1) ^ 1u));
+        TIC_PROF_WAIT(pw3, ptx::mbar_wait(&bars->reg_full, (uint32_t)(step & 1)));
         ptx::tc_fence_after();
         if (!(TIC_DBG_BITS(p1.dbg) & 1) && ptx::elect_one()) {
           const uint32_t dbase = tmem_base + 256u + b * 128u;
 #pragma unroll
           for (int sub = 0; sub < 4; ++sub) {
             const uint32_t aoff = (uint32_t)(((sub >> 1) * 16) * kFusedRegionCols + (sub & 1) * 8) * 64u;
-            const uint32_t ah = reg_d + (aoff >> 4), al = ah + (kFusedRegionPlane >> 4);
+            const uint32_t ah = reg_d + (aoff >> 4), al = ah + (kFusedRegionLoOff >> 4);
             const uint32_t d = dbase + (uint32_t)sub * 32u;
             uint32_t sp = 0, fresh = 0;
             u16_issue_plane_t<U16_DECONV_RGB, true, 2>(p2, ah, w2A_d, d, 2u * NPAD2, idesc2_st, a2_hi32, w2_hi32, tap2A >> 4, 0u, sp, fresh,
@@ -208,6 +267,12 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         }
         __syncwarp();
       }
+      TIC_PROF_ADD(0, pw0);
+      TIC_PROF_ADD(1, pw1);
+      TIC_PROF_ADD(2, pw2);
+      TIC_PROF_ADD(3, pw3);
+      TIC_PROF_ADD(4, TIC_PROF_NOW() - pt0);
+      TIC_PROF_ADD(5, nsteps);
     }
   } else if (warp >= 4) {
     // ===== epilogue warps.  Per tile, in this order:
@@ -220,11 +285,11 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     // per 32-pixel call, latency-bound), so its 32 calls per tile are spread over all sixteen warps.
     // warp = (TMEM lane quadrant, output phase (py, px)): 32 input pixels x one phase x 32 channels = two 16-column units
     const int q4 = warp & 3, py = ((warp - 4) >> 2) & 1, px = (warp - 4) >> 3;
-    const int e2_j = (warp - 4) >> 2;                   // epilogue 2: this warp takes (sub-tile, output row) units e2_j and e2_j + 4
+    const int e2_j = (warp - 4) >> 2;                   // epilogue 2: this warp takes sub-tile e2_j of its lane quadrant
     const int ph = py * 2 + px;
     const int m = q4 * 32 + lane, hh = m >> 3, xx = m & 7;
     const int e = tid - 128;                            // 0 .. 511 among the epilogue-1 threads
-    const uint32_t reg_hi = ptx::smem_u32(s_region), reg_lo = reg_hi + kFusedRegionPlane;
+    const uint32_t reg_hi = ptx::smem_u32(s_region), reg_lo = reg_hi + kFusedRegionLoOff;
     const uint32_t rowc = ptx::smem_u32(s_rowc), colc = ptx::smem_u32(s_colc);
     const uint32_t rowc_par = (uint32_t)fp.tiles_x * 16u * 128u;   // bytes of one parity of the row cache
     const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16);
@@ -232,20 +297,18 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const int R = 2 * hh + py, C = 2 * xx + px;         // region coordinates of this lane's output pixel
     const uint32_t pix = (uint32_t)((R + 1) * kFusedRegionCols + (C + 1)) * 64u;
     __half2 omax = __floats2half2_rn(0.f, 0.f);
-    int h_ones = 0, h_valid = 0;
-    // epilogue 2 of tile `estep` (patch en, tile ety / etx): two of the eight (sub-tile, output row) units of this quadrant
+    // epilogue 2 of tile `estep` (patch en, tile ety / etx): one of the four sub-tiles of this quadrant, both output rows
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0;
+    const long long pt0 = TIC_PROF_NOW();
     auto epilogue2 = [&](long long estep, int en, int ety, int etx) {
       const uint32_t b = (uint32_t)(estep & 1);
-      ptx::mbar_wait(&bars->acc2_full[b], (uint32_t)((estep >> 1) & 1));
+      TIC_PROF_WAIT(pw2, ptx::mbar_wait(&bars->acc2_full[b], (uint32_t)((estep >> 1) & 1)));
       ptx::tc_fence_after();
       const uint32_t tb = tmem_base + ((uint32_t)(q4 * 32) << 16) + 256u + b * 128u;
       if (!(TIC_DBG_BITS(p1.dbg) & 2)) {
-#pragma unroll 1
-        for (int k = 0; k < 2; ++k) {
-          const int u = e2_j + 4 * k, sub = u >> 1, half = u & 1;
-          u16_epilogue_tile<U16_DECONV_RGB>(a2, NPAD2, 0, 1, tb + (uint32_t)sub * 32u, en, ety * 32 + (sub >> 1) * 16 + hh,
-                                            etx * 16 + (sub & 1) * 8 + xx, en < fp.n, half, s_bias2, nullptr, h_ones, h_valid, omax, p2.cpad);
-        }
+        const int sub = e2_j;   // this warp's sub-tile of the 32 x 16 region
+        fused_rgb_epilogue(a2, tb + (uint32_t)sub * 32u, NPAD2, en, ety * 32 + (sub >> 1) * 16 + hh, etx * 16 + (sub & 1) * 8 + xx, en < fp.n,
+                           fp.bias2);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -262,7 +325,7 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         const uint32_t colc_rd = colc + (uint32_t)((tx + 1) & 1) * 4096u, colc_wr = colc + (uint32_t)(tx & 1) * 4096u;
         // ---- phase A (overlaps the previous tile's MMA2): accumulators -> registers, math, fp16 split; the TMEM buffer
         // goes back to the issuer at once, so MMA1 of the next tile queues behind the running MMA2 ----
-        ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1));
+        TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1)));
         ptx::tc_fence_after();
         uint32_t hp[2][8], lp[2][8];
 #pragma unroll
@@ -276,21 +339,15 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_leader(&bars->acc1_empty);
           }
-          const float4* bp = reinterpret_cast<const float4*>(s_bias1 + ci * 16);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b = bp[i];
-            v[4 * i] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i], 1.0f / 2048.0f, v[4 * i]), b.x), floor_v);
-            v[4 * i + 1] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 1], 1.0f / 2048.0f, v[4 * i + 1]), b.y), floor_v);
-            v[4 * i + 2] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 2], 1.0f / 2048.0f, v[4 * i + 2]), b.z), floor_v);
-            v[4 * i + 3] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 3], 1.0f / 2048.0f, v[4 * i + 3]), b.w), floor_v);
-          }
+          for (int i = 0; i < 16; ++i)
+            v[i] = fmaxf(__fadd_rn(__fmaf_rn(u[i], 1.0f / 2048.0f, v[i]), fp.bias1[ci * 16 + i]), floor_v);
 #pragma unroll
           for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[ci][i], lp[ci][i], omax);
         }
         // ---- phase B (the only part between two MMA2s): the previous tile's MMA2 has finished reading the region ----
-        ptx::mbar_wait(&bars->reg_empty, (uint32_t)(step & 1) ^ 1u);
-        asm volatile("bar.sync 2, 512;" ::: "memory");   // the previous tile's cache writes are visible to every epilogue-1 thread
+        TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->reg_empty, (uint32_t)(step & 1) ^ 1u));
+        TIC_PROF_WAIT(pw4, asm volatile("bar.sync 2, 512;" ::: "memory"));   // the previous tile's cache writes are visible to every epilogue-1 thread
         // halo: row -1 (17 pixels, corner first) and column -1 (32 pixels) of the region, 8 chunks of 16 B each
         if (e < 49 * 8 && !(TIC_DBG_BITS(p1.dbg) & 4)) {
           const int hp_ix = e >> 3, ch = e & 7;           // ch 0..3: hi plane, 4..7: lo' plane
@@ -309,10 +366,19 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
 #pragma unroll
         for (int ci = 0; ci < ((TIC_DBG_BITS(p1.dbg) & 4) ? 0 : 2); ++ci) {
           const uint32_t ah = reg_hi + pix + (uint32_t)ci * 32u, al = reg_lo + pix + (uint32_t)ci * 32u;
-          sts128(fused_swz64(ah), hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
-          sts128(fused_swz64(ah + 16u), hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
-          sts128(fused_swz64(al), lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
-          sts128(fused_swz64(al + 16u), lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+          {
+            // lanes xx < 4 store hi then lo', lanes xx >= 4 lo' then hi (kFusedRegionLoOff): eight bank groups per quarter-warp
+            const bool lo_first = (xx & 4) != 0;
+            const uint32_t a0 = lo_first ? al : ah, a1 = lo_first ? ah : al;
+            sts128(fused_swz64(a0), lo_first ? lp[ci][0] : hp[ci][0], lo_first ? lp[ci][1] : hp[ci][1], lo_first ? lp[ci][2] : hp[ci][2],
+                   lo_first ? lp[ci][3] : hp[ci][3]);
+            sts128(fused_swz64(a1), lo_first ? hp[ci][0] : lp[ci][0], lo_first ? hp[ci][1] : lp[ci][1], lo_first ? hp[ci][2] : lp[ci][2],
+                   lo_first ? hp[ci][3] : lp[ci][3]);
+            sts128(fused_swz64(a0 + 16u), lo_first ? lp[ci][4] : hp[ci][4], lo_first ? lp[ci][5] : hp[ci][5], lo_first ? lp[ci][6] : hp[ci][6],
+                   lo_first ? lp[ci][7] : hp[ci][7]);
+            sts128(fused_swz64(a1 + 16u), lo_first ? hp[ci][4] : lp[ci][4], lo_first ? hp[ci][5] : lp[ci][5], lo_first ? hp[ci][6] : lp[ci][6],
+                   lo_first ? hp[ci][7] : lp[ci][7]);
+          }
           if (R == 31) {   // last row of the region: halo row of the tile below (corner of the tile below-right)
             const uint32_t c0 = rowc_wr + (uint32_t)((tx * 16 + C) * 128 + ci * 32);
             sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
@@ -332,7 +398,7 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(&bars->reg_full);
         // ---- phase C: epilogue 2 of the previous tile ----
-        if (step > 0) epilogue2(step - 1, pn, pty, ptx_);
+        if (step > 0) TIC_PROF_WAIT(pw3, epilogue2(step - 1, pn, pty, ptx_));
         pn = (int)(2 * pp + rank);
         pty = ty;
         ptx_ = tx;
@@ -340,6 +406,15 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     }
     if (step > 0) epilogue2(step - 1, pn, pty, ptx_);
     if (ovf_hit(omax)) ovf_raise(a1.oflow);
+    if (warp == 4 || warp == 8) {
+      const int base = warp == 4 ? 16 : 24;
+      TIC_PROF_ADD(base + 0, pw0);
+      TIC_PROF_ADD(base + 1, pw1);
+      TIC_PROF_ADD(base + 2, pw2);
+      TIC_PROF_ADD(base + 3, pw3);
+      TIC_PROF_ADD(base + 4, pw4);
+      TIC_PROF_ADD(base + 5, TIC_PROF_NOW() - pt0);
+    }
   }
 
   ptx::tc_fence_before();
@@ -389,6 +464,7 @@ inline int u16_ensure_pair_weights(cudaStream_t stream, const float* w_dev, cons
 }
 
 inline int launch_fused_dec(cudaStream_t stream, const LayerArgs& a1, const LayerArgs& a2, const float* w1_dev, const float* w2_dev,
+                            const float* bias1_host, const float* bias2_host,
                             FusedDecWeights* fw, int num_sms, std::string* err, int* launches) {
   auto fail = [&](const std::string& what, int code) {
     if (err) *err = what;
@@ -418,6 +494,8 @@ inline int launch_fused_dec(cudaStream_t stream, const LayerArgs& a1, const Laye
   fp.tiles_y = a1.hin / 16;
   fp.tiles_pp = fp.tiles_x * fp.tiles_y;
   fp.pairs_total = ((long long)a1.n + 1) / 2;
+  for (int i = 0; i < 32; ++i) fp.bias1[i] = i < a1.cout ? bias1_host[i] : 0.f;
+  for (int i = 0; i < 4; ++i) fp.bias2[i] = i < a2.cout ? bias2_host[i] : 0.f;
   auto up = [](uint32_t v) { return (v + 1023u) & ~1023u; };
   uint32_t off = 0;
   fp.w1_off = off;

@@ -4,7 +4,7 @@
 // 12.9 GB of the encoder's 16.6 GB of HBM traffic, and encode_1 sits on the HBM roofline because of it.  Here it lives
 // in shared memory only:
 //
-//   TMA (raw u8 window of the image) -> builders (normalise through the split table, RGB0 fp16 quads, tic_first16.cuh)
+//   TMA (raw u8 window of the image) -> builders (normalise, fp16 split, RGB0 quads: the operand window of tic_first16.cuh)
 //   -> MMA1 (no-im2col windowed operands, four 16 x 8 sub-tiles) -> TMEM -> epilogue 1: bias, relu, fp16 split, written as
 //   the swizzled K-major stride-2 operand tile of the next layer -> MMA2 (nine taps) -> TMEM -> epilogue 2: bias, relu,
 //   fp16 split -> pair-plane output.
@@ -16,8 +16,12 @@
 // (zeros at the patch border = the conv's zero padding), so MMA1 does exactly the work of the unfused layer.
 //
 // Warps (832 threads, <= 78 registers): 0 raw-window TMA, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue
-// (four per TMEM lane quadrant: one first-layer sub-tile each; two of the four also take a 16-channel unit of epilogue 2
-// one tile behind), 20-25 builders.  TMEM: 4 x 64 columns for MMA1's sub-tiles, two buffers of 64 columns for MMA2.
+// (four per TMEM lane quadrant: one first-layer sub-tile each, and an eight-channel share of epilogue 2 one tile
+// behind), 20-25 builders.  TMEM: 4 x 64 columns for MMA1's sub-tiles, two buffers of 64 columns for MMA2.
+// Waiting: one warp of a group polls an mbarrier and releases the others through a named barrier, and a group's
+// arrivals are gathered by a named barrier into one mbarrier arrival per CTA — a warp parked in `mbarrier.try_wait`
+// is woken by every mbarrier event of the CTA and re-polls (7 instructions): with every warp polling and arriving for
+// itself 42 % of the kernel's executed instructions were polls (profiles/r2b).
 #pragma once
 #include "tic_first16.cuh"
 #include "tic_fused16.cuh"
@@ -34,7 +38,6 @@ constexpr uint32_t kFERawRow = 112;                             // bytes per raw
 constexpr uint32_t kFERawStage = 7424;                          // >= 65 * 112 = 7280, multiple of 128
 constexpr int kFERawStages = 2;
 constexpr uint32_t kFERegionPlane = 39936;                      // >= 17 * 2 * 9 * 128 = 39168, multiple of 1024
-constexpr int kFELutRep = 4;                                    // (8 in the stand-alone kernel; 12 KB less static shared memory here)
 constexpr uint32_t kFEStagePerWarp = 4096;                      // epilogue 2: hi | lo' plane of 32 pixels x 32 channels (TMA-store image)
 
 struct FusedEncParams {
@@ -46,6 +49,7 @@ struct FusedEncParams {
   const uint8_t* w1img;     // first-layer operand image, per CTA rank (f16_build_weights_s2_pair_kernel)
   uint32_t w1_off, w2_off, w2B_off, op_off, raw_off, region_off, rowc_off, colc_off, stage_off, bars_off;
   uint32_t smem_bytes;
+  float bias1[32];          // encode_0's bias as launch constants (constant-bank operands: no shared-memory loads in phase A)
 };
 
 struct FusedEncBars {
@@ -101,36 +105,28 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
   uint8_t* s_colc = smem + fp.colc_off;        // [parity][32 px][hi | lo]
   uint8_t* s_stage = smem + fp.stage_off;      // 4 x 4 KB: epilogue 2's TMA-store images (one per TMEM lane quadrant)
   FusedEncBars* bars = reinterpret_cast<FusedEncBars*>(smem + fp.bars_off);
-  __shared__ __align__(16) float s_bias1[32];
   __shared__ __align__(16) float s_bias2[32];
-  __shared__ uint32_t s_plut[3 * 256 * kFELutRep];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const bool leader = rank == 0;
 
-  if (tid < 32) {
-    s_bias1[tid] = tid < a1.cout ? a1.bias[tid] : 0.f;
-    s_bias2[tid] = tid < a2.cout ? a2.bias[tid] : 0.f;
-  }
-  for (int i = tid; i < 3 * 256 * kFELutRep; i += kFEThreads) {
-    __half hi, lo;
-    split16(a1.lut[i / kFELutRep], hi, lo);
-    s_plut[i] = pack_half2(hi, lo);
-  }
+  if (tid < 32) s_bias2[tid] = tid < a2.cout ? a2.bias[tid] : 0.f;
   for (int i = tid; i < 4608 / 16; i += kFEThreads)
     reinterpret_cast<uint4*>(s_w1)[i] = __ldg(reinterpret_cast<const uint4*>(fp.w1img + (size_t)rank * 4608) + i);
   if (tid == 0) {
     ptx::mbar_init(&bars->w_full, leader ? 2 : 1);
     for (int i = 0; i < kFERawStages; ++i) {
       ptx::mbar_init(&bars->raw_full[i], 1);
-      ptx::mbar_init(&bars->raw_empty[i], kFEBuilders);
+      ptx::mbar_init(&bars->raw_empty[i], 1);
     }
-    ptx::mbar_init(&bars->op_full, 2 * kFEBuilders);
+    // arrivals of a warp group are gathered with a named barrier first: one mbarrier arrival per CTA (every mbarrier event
+    // wakes every warp parked in a try_wait of this CTA, and sixteen warps arriving one by one kept the others polling)
+    ptx::mbar_init(&bars->op_full, 2);
     ptx::mbar_init(&bars->op_empty, 1);
     ptx::mbar_init(&bars->acc1_full, 1);
-    ptx::mbar_init(&bars->acc1_empty, 2 * 16);
-    ptx::mbar_init(&bars->reg_full, 2 * 16);
+    ptx::mbar_init(&bars->acc1_empty, 2);
+    ptx::mbar_init(&bars->reg_full, 2);
     ptx::mbar_init(&bars->reg_empty, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&bars->acc2_full[i], 1);
@@ -214,9 +210,11 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
       const uint32_t w2A_d = (ptx::smem_u32(s_w2A) >> 4) | (1u << 16), w2B_d = (ptx::smem_u32(s_w2B) >> 4) | (1u << 16);
       const uint32_t reg_d = (ptx::smem_u32(s_region) >> 4) | (1u << 16);
       ptx::mbar_wait(&bars->w_full, 0);
+      long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
+      const long long pt0 = TIC_PROF_NOW();
       auto mma1 = [&](long long step) {
-        ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u);
-        ptx::mbar_wait(&bars->op_full, (uint32_t)(step & 1));
+        TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u));
+        TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->op_full, (uint32_t)(step & 1)));
         ptx::tc_fence_after();
         if (!(TIC_DBG_BITS(p2.dbg) & 16) && ptx::elect_one()) {
 #pragma unroll
@@ -244,8 +242,8 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
       for (long long step = 0; step < nsteps; ++step) {
         if (step + 1 < nsteps) mma1(step + 1);
         const uint32_t b = (uint32_t)(step & 1);
-        ptx::mbar_wait(&bars->acc2_empty[b], (uint32_t)((step >> 1) & 1) ^ 1u);
-        ptx::mbar_wait(&bars->reg_full, (uint32_t)(step & 1));
+        TIC_PROF_WAIT(pw2, ptx::mbar_wait(&bars->acc2_empty[b], (uint32_t)((step >> 1) & 1) ^ 1u));
+        TIC_PROF_WAIT(pw3, ptx::mbar_wait(&bars->reg_full, (uint32_t)(step & 1)));
         ptx::tc_fence_after();
         if (!(TIC_DBG_BITS(p2.dbg) & 1) && ptx::elect_one()) {
           const uint32_t d = tmem_base + 256u + b * 64u;
@@ -262,61 +260,97 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
         }
         __syncwarp();
       }
+      TIC_PROF_ADD(0, pw0);
+      TIC_PROF_ADD(1, pw1);
+      TIC_PROF_ADD(2, pw2);
+      TIC_PROF_ADD(3, pw3);
+      TIC_PROF_ADD(4, TIC_PROF_NOW() - pt0);
+      TIC_PROF_ADD(5, nsteps);
     }
   } else if (warp >= kFEBuilderWarp0) {
     // ===== builders: raw u8 window -> normalised (hi, lo') RGB0 quads of the 65 x 34-pixel input window =====
-    // item = (row, quad of 4 pixels): 65 x 9 = 585 items over 192 lanes; out-of-patch pixels (the conv's zero padding) are 0
+    // The kernel sits on the shared-memory data pipe (ncu: LSU + tensor-core wavefronts = 92 % of its cycles), so the
+    // builders are written for wavefronts, not instructions: an item is (row, PAIR of pixels) — 65 x 17 = 1105 items,
+    // consecutive lanes take consecutive pairs.  Six raw bytes come from two aligned words (consecutive lanes: consecutive
+    // words), the normalisation (x - mean) / std is computed (f16_norm_fast: the correctly rounded quotient, same value as
+    // the 3 x 256 table of the stand-alone kernel whose twelve look-ups per quad cost a 3-way bank conflict each), and the
+    // two (hi, lo') quad pairs go out as one 16-byte store per plane at item * 16 — consecutive lanes, consecutive chunks.
     const int bl = (warp - kFEBuilderWarp0) * 32 + lane;
-    const uint32_t* const plut0 = s_plut + (lane & (kFELutRep - 1));
-    const uint32_t* const plut1 = plut0 + 256 * kFELutRep;
-    const uint32_t* const plut2 = plut1 + 256 * kFELutRep;
+    const float mean0 = a1.mean[0], mean1 = a1.mean[1], mean2 = a1.mean[2];
+    const float std0 = a1.stdv[0], std1 = a1.stdv[1], std2 = a1.stdv[2];
+    const float rstd0 = __frcp_rn(std0), rstd1 = __frcp_rn(std1), rstd2 = __frcp_rn(std2);
     long long step = 0;
+    long long pw0 = 0, pw1 = 0;
+    const long long pt0 = TIC_PROF_NOW();
+    // byte k of `w` as a float (exact): 0x4B0000bb is 8388608 + bb
+    auto byte_f = [](const uint32_t w, const uint32_t k) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | k)), 8388608.0f); };
+    auto build = [&](const int item, const uint32_t w0, const uint32_t w1, const int ty, const int tx) {
+      const int ry = item / 17, pp = item - ry * 17;
+      const uint32_t sh = (uint32_t)(pp & 1) * 16u;           // byte offset 6 * pp is 0 or 2 (mod 4)
+      const uint32_t lo32 = __funnelshift_r(w0, w1, sh);      // R0 G0 B0 R1
+      const uint32_t hi16 = w1 >> sh;                         // G1 B1
+      const bool row_ok = 64 * ty + ry < fp.P;
+      const int ix = 32 * tx + 2 * pp;
+      const bool ok0 = row_ok && ix < fp.P, ok1 = row_ok && ix + 1 < fp.P;
+      float r0 = f16_norm_fast(byte_f(lo32, 0), mean0, std0, rstd0), g0 = f16_norm_fast(byte_f(lo32, 1), mean1, std1, rstd1);
+      float b0 = f16_norm_fast(byte_f(lo32, 2), mean2, std2, rstd2), r1 = f16_norm_fast(byte_f(lo32, 3), mean0, std0, rstd0);
+      float g1 = f16_norm_fast(byte_f(hi16, 0), mean1, std1, rstd1), b1 = f16_norm_fast(byte_f(hi16, 1), mean2, std2, rstd2);
+      if (!ok0) r0 = g0 = b0 = 0.f;   // outside the patch: the conv's zero padding
+      if (!ok1) r1 = g1 = b1 = 0.f;
+      uint32_t h[4], l[4];
+      split16x2(r0, g0, h[0], l[0]);
+      split16x2(b0, 0.f, h[1], l[1]);
+      split16x2(r1, g1, h[2], l[2]);
+      split16x2(b1, 0.f, h[3], l[3]);
+      const uint32_t dst = ptx::smem_u32(s_op) + (uint32_t)item * 16u;   // row pitch 272 B = 17 pairs x 16 B
+      sts128(dst, h[0], h[1], h[2], h[3]);
+      sts128(dst + kFEOpPlane, l[0], l[1], l[2], l[3]);
+    };
+    constexpr int kItems = kFEOpRows * 17, kLanes = kFEBuilders * 32;
     for (long long pp = pair0; pp < fp.pairs_total; pp += npairs) {
       for (int t = 0; t < fp.tiles_pp; ++t, ++step) {
         int ty, tx;
         tile_of(t, ty, tx);
         const uint32_t r = (uint32_t)(step % kFERawStages);
-        ptx::mbar_wait(&bars->raw_full[r], (uint32_t)((step / kFERawStages) & 1));
-        ptx::mbar_wait(&bars->op_empty, (uint32_t)(step & 1) ^ 1u);   // MMA1 of the previous tile has read the operand buffer
-        const uint8_t* rawb = s_rawwin + (size_t)r * kFERawStage;
+        // one warp polls the mbarriers, the others park in the named barrier (no issue slots spent on waiting)
+        if (warp == kFEBuilderWarp0) {
+          TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->raw_full[r], (uint32_t)((step / kFERawStages) & 1)));
+          TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->op_empty, (uint32_t)(step & 1) ^ 1u));   // MMA1 of the previous tile has read the operand buffer
+        }
+        asm volatile("bar.sync 8, %0;" ::"n"(kFEBuilders * 32) : "memory");
+        const uint32_t rawb = ptx::smem_u32(s_rawwin + (size_t)r * kFERawStage);
         if (!(TIC_DBG_BITS(p2.dbg) & 8)) {
+          // two independent items per pass: their shared-memory round trips overlap
 #pragma unroll 1
-          for (int item = bl; item < kFEOpRows * 9; item += kFEBuilders * 32) {
-            const int ry = item / 9, qx = item - ry * 9;
-            const int iy = 64 * ty + ry, ix = 32 * tx + 4 * qx;
-            const uint32_t* rp = reinterpret_cast<const uint32_t*>(rawb + (uint32_t)ry * kFERawRow + (uint32_t)qx * 12u);
-            const uint32_t w0 = rp[0], w1 = rp[1], w2 = rp[2];
-            uint2 vh[4], vl[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t b0 = j == 0 ? (w0 & 0xffu) : j == 1 ? (w0 >> 24) : j == 2 ? ((w1 >> 16) & 0xffu) : ((w2 >> 8) & 0xffu);
-              const uint32_t b1 = j == 0 ? ((w0 >> 8) & 0xffu) : j == 1 ? (w1 & 0xffu) : j == 2 ? (w1 >> 24) : ((w2 >> 16) & 0xffu);
-              const uint32_t b2 = j == 0 ? ((w0 >> 16) & 0xffu) : j == 1 ? ((w1 >> 8) & 0xffu) : j == 2 ? (w2 & 0xffu) : (w2 >> 24);
-              const bool okj = iy < fp.P && ix + j < fp.P;
-              const uint32_t x0 = okj ? plut0[b0 * kFELutRep] : 0u;
-              const uint32_t x1 = okj ? plut1[b1 * kFELutRep] : 0u;
-              const uint32_t x2 = okj ? plut2[b2 * kFELutRep] : 0u;
-              vh[j] = make_uint2(__byte_perm(x0, x1, 0x5410), x2 & 0xffffu);
-              vl[j] = make_uint2(__byte_perm(x0, x1, 0x7632), x2 >> 16);
-            }
-            uint8_t* st = s_op + (uint32_t)ry * kFEOpPitch + (uint32_t)(4 * qx) * 8u;
-            const int npx = qx == 8 ? 2 : 4;   // the window is 34 pixels wide
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (j < npx) {
-                *reinterpret_cast<uint2*>(st + j * 8) = vh[j];
-                *reinterpret_cast<uint2*>(st + kFEOpPlane + j * 8) = vl[j];
-              }
-            }
+          for (int item = bl; item < kItems; item += 2 * kLanes) {
+            const int itemB = item + kLanes;
+            const bool hasB = itemB < kItems;
+            const int ryA = item / 17, ppA = item - ryA * 17;
+            const int ryB = hasB ? itemB / 17 : ryA, ppB = hasB ? itemB - ryB * 17 : ppA;
+            const uint32_t adA = rawb + (uint32_t)ryA * kFERawRow + ((uint32_t)(6 * ppA) & ~3u);
+            const uint32_t adB = rawb + (uint32_t)ryB * kFERawRow + ((uint32_t)(6 * ppB) & ~3u);
+            const uint32_t a0 = lds32(adA), a1w = lds32(adA + 4u), b0 = lds32(adB), b1w = lds32(adB + 4u);
+            build(item, a0, a1w, ty, tx);
+            if (hasB) build(itemB, b0, b1w, ty, tx);
           }
         }
         ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(&bars->raw_empty[r]);
-          ptx::mbar_arrive_leader(&bars->op_full);
+        // the warp with the longest item list gathers the others and arrives once
+        if (warp == kFEBuilderWarp0) {
+          asm volatile("bar.sync 9, %0;" ::"n"(kFEBuilders * 32) : "memory");
+          if (lane == 0) {
+            ptx::mbar_arrive(&bars->raw_empty[r]);
+            ptx::mbar_arrive_leader(&bars->op_full);
+          }
+        } else {
+          asm volatile("bar.arrive 9, %0;" ::"n"(kFEBuilders * 32) : "memory");
         }
       }
+    }
+    if (warp == kFEBuilderWarp0) {
+      TIC_PROF_ADD(8, pw0);
+      TIC_PROF_ADD(9, pw1);
+      TIC_PROF_ADD(10, TIC_PROF_NOW() - pt0);
     }
   } else if (warp >= 4 && warp < kFEBuilderWarp0) {
     // ===== epilogue warps.  Per tile: A  first-layer accumulators -> registers, bias, relu, fp16 split (overlaps the
@@ -335,22 +369,58 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     auto cell = [](int r, int c) { return (uint32_t)((((r >> 1) * 2 + (r & 1)) * 9 + (c >> 1)) * 128 + (c & 1) * 64); };
     const uint32_t pix = cell(R, C);
     __half2 omax = __floats2half2_rn(0.f, 0.f);
-    int h_ones = 0, h_valid = 0;
-    // epilogue 2 (one warp per TMEM lane quadrant: the warps of sub-tile 0): the first layer's TMA-store epilogue
-    // (tic_first16.cuh) on encode_1's accumulators — 32 pixels x 32 channels, both planes staged, two bulk tensor stores
-    const bool e2_warp = sub == 0;
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0;
+    const long long pt0 = TIC_PROF_NOW();
+    // epilogue 2, one tile behind, shared by all sixteen warps (on the four warps of sub-tile 0 alone it took 2400 cycles
+    // of a 6100-cycle step and everything else waited for them): the four warps of a TMEM lane quadrant take eight of
+    // encode_1's 32 channels each — one 16-byte chunk per pixel and plane of the quadrant's TMA-store image
+    // (tic_first16.cuh: 32 pixels x 64 B, 64-byte swizzle) — and the warp of sub-tile 0 stores both planes.
     const uint32_t stage2 = ptx::smem_u32(s_stage + (size_t)q4 * kFEStagePerWarp);
+    const uint32_t stage_px = stage2 + (uint32_t)lane * 64u + (uint32_t)((sub ^ ((lane >> 1) & 3)) << 4);
+    const float floor2 = a2.act ? 0.0f : -INFINITY;
     auto epilogue2 = [&](long long estep, long long en, int ety, int etx) {
       const uint32_t b = (uint32_t)(estep & 1);
-      ptx::mbar_wait(&bars->acc2_full[b], (uint32_t)((estep >> 1) & 1));
+      // (already complete: phase B of this step waited for the same MMA2; a first-try success, no polling)
+      TIC_PROF_WAIT(pw2, ptx::mbar_wait(&bars->acc2_full[b], (uint32_t)((estep >> 1) & 1)));
       ptx::tc_fence_after();
       if (!(TIC_DBG_BITS(p2.dbg) & 2)) {
-        f16_t2_epilogue_tile<32>(a2, &tm_ohi, &tm_olo, tq + 256u + b * 64u, NPAD2, (int)en, ety * 16 + 4 * q4, etx * 8, s_bias2, stage2, lane,
-                                 &bars->acc2_empty[b], omax, /*rel_leader=*/true, /*store=*/en < fp.n);
+        float v[8], u[8];
+        const uint32_t tb = tq + 256u + b * 64u + (uint32_t)(sub * 8);
+        ptx::tmem_ld8_nowait(tb + (uint32_t)NPAD2, u);
+        ptx::tmem_ld8_nowait(tb, v);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias2 + sub * 8), b1 = *reinterpret_cast<const float4*>(s_bias2 + sub * 8 + 4);
+        v[0] = fmaxf(__fadd_rn(__fmaf_rn(u[0], 1.0f / 2048.0f, v[0]), b0.x), floor2);
+        v[1] = fmaxf(__fadd_rn(__fmaf_rn(u[1], 1.0f / 2048.0f, v[1]), b0.y), floor2);
+        v[2] = fmaxf(__fadd_rn(__fmaf_rn(u[2], 1.0f / 2048.0f, v[2]), b0.z), floor2);
+        v[3] = fmaxf(__fadd_rn(__fmaf_rn(u[3], 1.0f / 2048.0f, v[3]), b0.w), floor2);
+        v[4] = fmaxf(__fadd_rn(__fmaf_rn(u[4], 1.0f / 2048.0f, v[4]), b1.x), floor2);
+        v[5] = fmaxf(__fadd_rn(__fmaf_rn(u[5], 1.0f / 2048.0f, v[5]), b1.y), floor2);
+        v[6] = fmaxf(__fadd_rn(__fmaf_rn(u[6], 1.0f / 2048.0f, v[6]), b1.z), floor2);
+        v[7] = fmaxf(__fadd_rn(__fmaf_rn(u[7], 1.0f / 2048.0f, v[7]), b1.w), floor2);
+        uint32_t h4[4], l4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split16x2(v[2 * i], v[2 * i + 1], h4[i], l4[i], omax);
+        sts128(stage_px, h4[0], h4[1], h4[2], h4[3]);
+        sts128(stage_px + kT2LoOff, l4[0], l4[1], l4[2], l4[3]);
+        ptx::fence_proxy_async_smem();   // generic-proxy stage writes -> visible to the TMA store
       } else {
         ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_leader(&bars->acc2_empty[b]);
+      }
+      // quadrant barrier 10 + q4: the warp of sub-tile 0 gathers the other three, hands the accumulators back and stores
+      if (sub == 0) {
+        asm volatile("bar.sync %0, 128;" ::"r"(10 + q4) : "memory");
+        if (lane == 0) {
+          ptx::mbar_arrive_leader(&bars->acc2_empty[b]);
+          if (en < fp.n && !(TIC_DBG_BITS(p2.dbg) & 2)) {
+            ptx::tma_store_4d_s(&tm_ohi, stage2, 0, etx * 8, ety * 16 + 4 * q4, (int)en);
+            ptx::tma_store_4d_s(&tm_olo, stage2 + kT2LoOff, 0, etx * 8, ety * 16 + 4 * q4, (int)en);
+            ptx::bulk_commit_group();
+          }
+        }
+      } else {
+        asm volatile("bar.arrive %0, 128;" ::"r"(10 + q4) : "memory");
       }
     };
     long long step = 0, pn = 0;
@@ -365,7 +435,9 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
         const uint32_t colc_rd = colc + (uint32_t)((tx + 1) & 1) * 4096u, colc_wr = colc + (uint32_t)(tx & 1) * 4096u;
         const bool has_below = ty + 1 < fp.tiles_y, has_right = tx + 1 < fp.tiles_x;
         // ---- phase A ----
-        ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1));
+        // one warp polls, the rest parks in a named barrier (every polling warp costs issue slots)
+        if (warp == 8) TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1)));
+        asm volatile("bar.sync 3, 512;" ::: "memory");
         ptx::tc_fence_after();
         uint32_t hp[2][8], lp[2][8];
 #pragma unroll
@@ -374,26 +446,26 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
           ptx::tmem_ld16_nowait(tbuf1 + (uint32_t)(32 + ci * 16), u);
           ptx::tmem_ld16_nowait(tbuf1 + (uint32_t)(ci * 16), v);
           ptx::tmem_ld_wait();
-          if (ci == 1) {
+          if (ci == 1) {   // last TMEM read: one warp gathers the group and arrives once
             ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_leader(&bars->acc1_empty);
+            if (warp == 4) {
+              asm volatile("bar.sync 6, 512;" ::: "memory");
+              if (lane == 0) ptx::mbar_arrive_leader(&bars->acc1_empty);
+            } else {
+              asm volatile("bar.arrive 6, 512;" ::: "memory");
+            }
           }
-          const float4* bp = reinterpret_cast<const float4*>(s_bias1 + ci * 16);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b = bp[i];
-            v[4 * i] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i], 1.0f / 2048.0f, v[4 * i]), b.x), floor1);
-            v[4 * i + 1] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 1], 1.0f / 2048.0f, v[4 * i + 1]), b.y), floor1);
-            v[4 * i + 2] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 2], 1.0f / 2048.0f, v[4 * i + 2]), b.z), floor1);
-            v[4 * i + 3] = fmaxf(__fadd_rn(__fmaf_rn(u[4 * i + 3], 1.0f / 2048.0f, v[4 * i + 3]), b.w), floor1);
-          }
+          for (int i = 0; i < 16; ++i)
+            v[i] = fmaxf(__fadd_rn(__fmaf_rn(u[i], 1.0f / 2048.0f, v[i]), fp.bias1[ci * 16 + i]), floor1);
 #pragma unroll
           for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[ci][i], lp[ci][i], omax);
         }
         // ---- phase B ----
-        ptx::mbar_wait(&bars->reg_empty, (uint32_t)(step & 1) ^ 1u);
-        asm volatile("bar.sync 2, 512;" ::: "memory");   // the previous tile's cache writes are visible
+        if (warp == 8) TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->reg_empty, (uint32_t)(step & 1) ^ 1u));
+        if (sub == 0 && lane == 0) ptx::bulk_wait_group_read<0>();   // this quadrant's previous TMA store has read the stage
+        // region free; the previous tile's cache writes are visible; the stage may be rewritten in phase C
+        TIC_PROF_WAIT(pw4, asm volatile("bar.sync 2, 512;" ::: "memory"));
         // halo: row 32 (17 pixels, corner last) and column 16 (32 pixels) of the region, 8 chunks of 16 B each
         if (e < 49 * 8 && !(TIC_DBG_BITS(p2.dbg) & 4)) {
           const int hx = e >> 3, ch = e & 7;              // ch 0..3: hi plane, 4..7: lo' plane
@@ -432,18 +504,35 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
           }
         }
         ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_leader(&bars->reg_full);
+        if (warp == 8) {
+          asm volatile("bar.sync 7, 512;" ::: "memory");
+          if (lane == 0) ptx::mbar_arrive_leader(&bars->reg_full);
+        } else {
+          asm volatile("bar.arrive 7, 512;" ::: "memory");
+        }
         // ---- phase C: epilogue 2 of the previous tile ----
-        if (e2_warp && step > 0) epilogue2(step - 1, pn, pty, ptx_);
+        if (step > 0) TIC_PROF_WAIT(pw3, epilogue2(step - 1, pn, pty, ptx_));
         pn = 2 * pp + rank;
         pty = ty;
         ptx_ = tx;
       }
     }
-    if (e2_warp && step > 0) epilogue2(step - 1, pn, pty, ptx_);
-    if (e2_warp && lane == 0) ptx::bulk_wait_group<0>();   // every TMA store of this warp is complete before the CTA may exit
+    if (step > 0) {
+      if (sub == 0 && lane == 0) ptx::bulk_wait_group_read<0>();
+      asm volatile("bar.sync 2, 512;" ::: "memory");
+      epilogue2(step - 1, pn, pty, ptx_);
+    }
+    if (sub == 0 && lane == 0) ptx::bulk_wait_group<0>();   // every TMA store of this warp is complete before the CTA may exit
     if (ovf_hit(omax)) ovf_raise(a1.oflow);
+    if (warp == 4 || warp == 8) {   // an epilogue-2 warp and a plain one
+      const int base = warp == 4 ? 16 : 24;
+      TIC_PROF_ADD(base + 0, pw0);
+      TIC_PROF_ADD(base + 1, pw1);
+      TIC_PROF_ADD(base + 2, pw2);
+      TIC_PROF_ADD(base + 3, pw3);
+      TIC_PROF_ADD(base + 4, pw4);
+      TIC_PROF_ADD(base + 5, TIC_PROF_NOW() - pt0);
+    }
   }
 
   ptx::tc_fence_before();
@@ -477,6 +566,7 @@ struct FusedEncWeights {
 };
 
 inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const LayerArgs& a2, const float* w1_dev, const float* w2_dev,
+                            const float* bias1_host,
                             FusedEncWeights* fw, int num_sms, std::string* err, int* launches) {
   auto fail = [&](const std::string& what, int code) {
     if (err) *err = what;
@@ -507,6 +597,7 @@ inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const Laye
   fp.tiles_pp = fp.tiles_x * fp.tiles_y;
   fp.pairs_total = ((long long)a1.n + 1) / 2;
   fp.w1img = fw->w1;
+  for (int i = 0; i < 32; ++i) fp.bias1[i] = i < a1.cout ? bias1_host[i] : 0.f;
   auto up = [](uint32_t v) { return (v + 1023u) & ~1023u; };
   uint32_t off = 0;
   fp.w1_off = off;
@@ -530,7 +621,7 @@ inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const Laye
   fp.bars_off = off;
   off += (uint32_t)sizeof(FusedEncBars);
   fp.smem_bytes = off + 1024u;
-  if (fp.smem_bytes + 13312u /* static: table, biases */ > 227u * 1024u) return fail("fused encoder: shared memory plan does not fit", -5);
+  if (fp.smem_bytes + 1024u /* static: bias, alignment */ > 227u * 1024u) return fail("fused encoder: shared memory plan does not fit", -5);
 
   // raw image windows: 3-D map over [B, H, W * 3] bytes, box 65 rows x 112 bytes
   CUtensorMap tm_img, tm_o[2];

@@ -10,6 +10,10 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import tf_image_compression_b200 as T
+from tf_image_compression_b200 import _lib as _L
+
+_L.LIB_PATH = _L.LIB_PATH.with_name("libtic_ablate.so")   # tools/build_ablate.sh; the package itself never loads it
+assert _L.LIB_PATH.exists(), "run tools/build_ablate.sh first"
 
 which = sys.argv[1] if len(sys.argv) > 1 else "dec"
 mean = np.array([118.3, 113.9, 102.6], np.float32)

@@ -369,7 +369,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     auto cell = [](int r, int c) { return (uint32_t)((((r >> 1) * 2 + (r & 1)) * 9 + (c >> 1)) * 128 + (c & 1) * 64); };
     const uint32_t pix = cell(R, C);
     __half2 omax = __floats2half2_rn(0.f, 0.f);
-    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0;
+    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0, pw5 = 0, pw6 = 0, pw7 = 0, pw8 = 0;
     const long long pt0 = TIC_PROF_NOW();
     // epilogue 2, one tile behind, shared by all sixteen warps (on the four warps of sub-tile 0 alone it took 2400 cycles
     // of a 6100-cycle step and everything else waited for them): the four warps of a TMEM lane quadrant take eight of
@@ -437,7 +437,8 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
         // ---- phase A ----
         // one warp polls, the rest parks in a named barrier (every polling warp costs issue slots)
         if (warp == 8) TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1)));
-        asm volatile("bar.sync 3, 512;" ::: "memory");
+        TIC_PROF_WAIT(pw5, asm volatile("bar.sync 3, 512;" ::: "memory"));
+        const long long pta = TIC_PROF_NOW();
         ptx::tc_fence_after();
         uint32_t hp[2][8], lp[2][8];
 #pragma unroll
@@ -449,7 +450,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
           if (ci == 1) {   // last TMEM read: one warp gathers the group and arrives once
             ptx::tc_fence_before();
             if (warp == 4) {
-              asm volatile("bar.sync 6, 512;" ::: "memory");
+              TIC_PROF_WAIT(pw6, asm volatile("bar.sync 6, 512;" ::: "memory"));
               if (lane == 0) ptx::mbar_arrive_leader(&bars->acc1_empty);
             } else {
               asm volatile("bar.arrive 6, 512;" ::: "memory");
@@ -462,10 +463,12 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
           for (int i = 0; i < 8; ++i) split16x2(v[2 * i], v[2 * i + 1], hp[ci][i], lp[ci][i], omax);
         }
         // ---- phase B ----
+        pw7 += TIC_PROF_NOW() - pta;   // phase A
         if (warp == 8) TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->reg_empty, (uint32_t)(step & 1) ^ 1u));
         if (sub == 0 && lane == 0) ptx::bulk_wait_group_read<0>();   // this quadrant's previous TMA store has read the stage
         // region free; the previous tile's cache writes are visible; the stage may be rewritten in phase C
         TIC_PROF_WAIT(pw4, asm volatile("bar.sync 2, 512;" ::: "memory"));
+        const long long ptb = TIC_PROF_NOW();
         // halo: row 32 (17 pixels, corner last) and column 16 (32 pixels) of the region, 8 chunks of 16 B each
         if (e < 49 * 8 && !(TIC_DBG_BITS(p2.dbg) & 4)) {
           const int hx = e >> 3, ch = e & 7;              // ch 0..3: hi plane, 4..7: lo' plane
@@ -504,8 +507,9 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
           }
         }
         ptx::fence_proxy_async_smem();
+        pw8 += TIC_PROF_NOW() - ptb;   // phase B
         if (warp == 8) {
-          asm volatile("bar.sync 7, 512;" ::: "memory");
+          TIC_PROF_WAIT(pw6, asm volatile("bar.sync 7, 512;" ::: "memory"));
           if (lane == 0) ptx::mbar_arrive_leader(&bars->reg_full);
         } else {
           asm volatile("bar.arrive 7, 512;" ::: "memory");
@@ -532,7 +536,12 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
       TIC_PROF_ADD(base + 3, pw3);
       TIC_PROF_ADD(base + 4, pw4);
       TIC_PROF_ADD(base + 5, TIC_PROF_NOW() - pt0);
+      TIC_PROF_ADD(base + 16, pw5);
+      TIC_PROF_ADD(base + 17, pw6);
+      TIC_PROF_ADD(base + 18, pw7);
+      TIC_PROF_ADD(base + 19, pw8);
     }
+    (void)pw5; (void)pw6; (void)pw7; (void)pw8;
   }
 
   ptx::tc_fence_before();

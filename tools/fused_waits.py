@@ -48,7 +48,9 @@ names = {0: "issuer  wait acc1_empty", 1: "issuer  wait op_full / in_full", 2: "
          16: "epi w4  wait acc1_full", 17: "epi w4  wait reg_empty", 18: "epi w4  wait acc2_full (inside phase C)", 19: "epi w4  phase C total",
          20: "epi w4  bar.sync", 21: "epi w4  total",
          24: "epi w8  wait acc1_full", 25: "epi w8  wait reg_empty", 26: "epi w8  wait acc2_full (inside phase C)", 27: "epi w8  phase C total",
-         28: "epi w8  bar.sync", 29: "epi w8  total"}
+         28: "epi w8  bar.sync", 29: "epi w8  total",
+         32: "epi w4  bar.sync 3 (acc1_full release)", 33: "epi w4  gather barrier (acc1_empty)", 34: "epi w4  phase A", 35: "epi w4  phase B",
+         40: "epi w8  bar.sync 3 (acc1_full release)", 41: "epi w8  gather barrier (reg_full)", 42: "epi w8  phase A", 43: "epi w8  phase B"}
 print(f"fused {which}: {steps} steps in cluster 0; cycles per step")
 for k in sorted(names):
     if v[k]:

@@ -184,15 +184,6 @@ __device__ __forceinline__ void stage_tiles(const LayerArgs& a, const SmemPlan& 
 // ---- last-layer / activation stores (epilogue fusion) --------------------------------------
 // v[NV] = accumulator + bias already activated (+ residual) for channels oc .. oc+NV-1 of
 // output pixel (n, y, x).  s_hist: CTA-private symbol histogram.
-// tic_quantize_symbol (include/tic_math.h: rint(sigmoid(x) * (q - 1))) with a shortcut for the binary quantiser of every
-// shipped config: for |x| > 1e-4 the fp32 sigmoid is at least 2.4e-5 (400 ulp) away from 0.5, so the symbol is the sign
-// of the logit; closer to zero (and for NaN) the full expression decides.  Same symbols, without the exp and the
-// division for all but ~1 in 10^4 elements (the quantiser epilogue was 0.09 of encode_4's 0.23 ms).
-__device__ __forceinline__ int quantize_symbol_fast(const float x, const int q) {
-  if (q == 2 && fabsf(x) > 1e-4f) return x > 0.0f ? 1 : 0;
-  return tic_quantize_symbol(x, q);
-}
-
 template <int NV>
 __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, int x, int oc, const float* v,
                                             unsigned* s_hist, int& ones, int& valid) {
@@ -246,7 +237,7 @@ __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, in
         uint32_t w[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
-          const int s = quantize_symbol_fast(v[i], a.q);
+          const int s = tic_quantize_symbol(v[i], a.q);
           w[i >> 2] |= (uint32_t)s << (8 * (i & 3));
           if (a.q == 2) {
             ones += s;
@@ -261,7 +252,7 @@ __device__ __forceinline__ void store_pixel(const LayerArgs& a, int n, int y, in
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (oc + i < a.cout) {
-          int s = quantize_symbol_fast(v[i], a.q);
+          int s = tic_quantize_symbol(v[i], a.q);
           if (a.out_mode == IO_QUANT_U8)
             reinterpret_cast<uint8_t*>(a.out)[gp * a.cout + oc + i] = (uint8_t)s;
           else

@@ -1133,6 +1133,8 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
       const uint32_t b = ti & ((uint32_t)p.nbuf - 1u);
       const uint32_t use = ti >> p.nbshift;
+      ptx::mbar_wait(&bars->acc_full[b], use & 1);
+      ptx::tc_fence_after();
       long long tt = 2 * tp + rank;
       uint32_t tq, tx, ty, tn;
       fast_divmod((uint32_t)tt, p.tx_d, tq, tx);
@@ -1140,15 +1142,6 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const int n = (int)tn * p.bn + nb;
       const int yt = (int)ty * p.bh + hh, xt = (int)tx * 8 + xx;
       const bool valid = n < p.n;
-      if (MODE != U16_DECONV && !u16_is_ph(MODE) && a.res && a.res16 && valid) {
-        // residual rows of this lane's pixel (both planes) on their way to L2 while the tile's MMAs still run: the
-        // residual was written two layers ago and has left the cache; the epilogue's loads were exposed HBM latency
-        const __half* r = reinterpret_cast<const __half*>(a.res) + (((long long)n * a.hout + yt) * a.wout + xt) * a.cout + p.oc0;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(r));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(r + a.res_lo_off));
-      }
-      ptx::mbar_wait(&bars->acc_full[b], use & 1);
-      ptx::tc_fence_after();
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
       if (TIC_DBG_BITS(p.dbg) & 4) {
       } else if (p.staged) {

@@ -48,6 +48,44 @@ def test_decoder_parity_at_realistic_range(variant, mode):
     codec.close()
 
 
+# ---- fused layer pairs (tic_fused_enc16.cuh / tic_fused16.cuh) on the shapes that stress their tiling ----------------
+@pytest.mark.parametrize("variant,P,h,w,nimg", [("model_0", 64, 64, 192, 1),       # one tile row per patch, 3 patches (odd)
+                                                ("model_0", 128, 128, 384, 3),     # 9 patches: pairs straddle images, odd tail
+                                                ("model_0", 256, 256, 512, 1),     # eight tile columns (the maximum)
+                                                ("base_model/input_256", 256, 256, 256, 3),
+                                                ("model_1", 128, 256, 128, 1)])
+def test_fused_layer_pairs_on_edge_shapes(variant, P, h, w, nimg):
+    """compute = tensor, u8 images whose patch grid covers them exactly: the first two encoder layers and the last two
+    decoder layers run as the back-to-back kernels.  A CTA pair walks two patches in lock-step, so odd patch counts leave
+    a pair with one patch beyond the batch; P = 64 has a single tile row (no halo row from below / above), P = 256 the
+    maximum number of tile columns.  Symbols and reconstruction against the oracle, and against the fp32 CUDA-core path."""
+    codec, enc, dec = make_codec(variant, "fanin", compute="tensor")
+    imgs = np.stack([O.synthetic_image(h, w, 40 + i) for i in range(nimg)])
+    patches = np.stack([pt for im in imgs for pt in O.crop_image_input_patches(im, P)])
+    sym = codec.encode_images(imgs, P)
+    ref = O.encoder(patches.astype(np.float32), variant, enc, MEAN, STD, 2)
+    got = sym.reshape(ref.shape)
+    nm = int((got != ref).sum())
+    assert nm <= max(1, int(2e-5 * ref.size)), f"{variant}@{P}: {nm}/{ref.size} symbol mismatches"
+    rec = codec.decode_images(ref.reshape(sym.shape), h, w, P, out_dtype=np.float32)
+    rref = O.decoder(ref, variant, dec, MEAN, STD, 2)
+    per = patches.shape[0] // nimg
+    for i in range(nimg):
+        full = T.utils.concat_patches(list(rref[i * per:(i + 1) * per]), h, w, P)
+        err = float(np.abs(rec[i] - full).max())
+        assert err <= 1e-3, (variant, P, i, err)
+    rec_u8 = codec.decode_images(ref.reshape(sym.shape), h, w, P)
+    assert np.abs(rec_u8.astype(int) - np.around(rec).astype(int)).max() == 0
+    # the same calls on the CUDA-core fp32 path (no fused kernels)
+    codec.set_compute("fp32")
+    sym32 = codec.encode_images(imgs, P)
+    assert int((sym32 != sym).sum()) <= max(1, int(2e-5 * ref.size))
+    rec32 = codec.decode_images(ref.reshape(sym.shape), h, w, P, out_dtype=np.float32)
+    assert float(np.abs(rec32 - rec).max()) <= 1e-3
+    print(f"[fused pairs {variant}@{P} {nimg}x{h}x{w}] symbol mismatches {nm}/{ref.size}")
+    codec.close()
+
+
 # ---- the first tensor path: 3xTF32 (error-compensated) and single-pass TF32 (VERDICT r1, weak #4) ----------------
 def test_tf32_compute_modes():
     """TIC_COMPUTE_TENSOR_3XTF32 meets the same bars as the fp32 path; TIC_COMPUTE_TENSOR_TF32 is the documented fast

@@ -1240,7 +1240,7 @@ struct U16Plan {
 };
 
 // Geometry + shared-memory plan for one slice width; returns false if it does not fit.
-inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out, bool pair = false) {
+inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out, bool pair = false, bool allow_ph = true) {
   U16Params p{};
   p.pair = pair ? 1 : 0;
   p.mode = u16_mode_of(kind, stride);
@@ -1259,7 +1259,7 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   p.KB = a.cin / p.kc;
   p.ksteps = p.kc / 16;
   p.npad = (cs + 15) / 16 * 16;
-  if (p.mode == U16_DECONV && cs <= 32) {
+  if (p.mode == U16_DECONV && cs <= 32 && (allow_ph || a.cout <= 32)) {
     p.mode = U16_DECONV_PH;
     p.cpad = cs <= 4 ? 4 : (cs + 15) / 16 * 16;
     p.npad = (4 * p.cpad + 15) / 16 * 16;  // N = (phase, channel)
@@ -1383,10 +1383,16 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
   int cs = std::min(a.cout, 128);
   // (64-channel transposed conv as two phase-stacked 32-channel slices measured slower than tap-based: 0.51 vs 0.43 ms)
   if (kind == 1 && tic_env_set("TIC_DECONV_PH_SLICES")) cs = std::min(cs, 32);
+  // (ablation builds) tap-based slices of 32 output channels: two TMEM buffers instead of one (the unsliced 64-channel
+  // tile needs all 512 columns, so its MMAs and its epilogue alternate).  Measured on decode_3: 2 x 0.205 ms against
+  // 0.414 ms unsliced, identical output — the layer is bound by its epilogue's 16-byte strided stores, not by the
+  // missing overlap, so the default stays one launch.
+  const bool tap_slices = kind == 1 && a.cout == 64 && tic_env_int("TIC_DECONV_TAP_SLICES", 0) != 0;
+  if (tap_slices) cs = std::min(cs, 32);
   cs = (cs + 15) / 16 * 16;
   bool ok = false;
   for (; cs >= 16; cs -= 16)
-    if ((ok = u16_plan(a, kind, stride, std::min(cs, a.cout), &plan, pair))) break;
+    if ((ok = u16_plan(a, kind, stride, std::min(cs, a.cout), &plan, pair, !tap_slices))) break;
   if (!ok) return fail("layer does not fit the fp16-pair tensor path", -5);
   cs = plan.cs;
 
@@ -1423,7 +1429,7 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
     if (si >= 16) return fail("too many output-channel slices", -5);
     const int csl = std::min(cs, a.cout - oc0);
     U16Plan pl{};
-    if (!u16_plan(a, kind, stride, csl, &pl, pair)) return fail("slice plan failed", -5);
+    if (!u16_plan(a, kind, stride, csl, &pl, pair, !tap_slices)) return fail("slice plan failed", -5);
     U16Params p = pl.p;
     p.oc0 = oc0;
     U16WeightSlice* ws = &uw->slice[si];

@@ -216,8 +216,8 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
       const uint32_t w2A_d = (ptx::smem_u32(s_w2A) >> 4) | (1u << 16), w2B_d = (ptx::smem_u32(s_w2B) >> 4) | (1u << 16);
       const uint32_t reg_d = (ptx::smem_u32(s_region) >> 4) | (1u << 16);
       ptx::mbar_wait(&bars->w_full, 0);
-      long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
-      const long long pt0 = TIC_PROF_NOW();
+      [[maybe_unused]] long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
+      [[maybe_unused]] const long long pt0 = TIC_PROF_NOW();
       auto mma1 = [&](long long step) {
         const uint32_t s = (uint32_t)(step & 1);
         TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u));
@@ -298,8 +298,8 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t pix = (uint32_t)((R + 1) * kFusedRegionCols + (C + 1)) * 64u;
     __half2 omax = __floats2half2_rn(0.f, 0.f);
     // epilogue 2 of tile `estep` (patch en, tile ety / etx): one of the four sub-tiles of this quadrant, both output rows
-    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0;
-    const long long pt0 = TIC_PROF_NOW();
+    [[maybe_unused]] long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0;
+    [[maybe_unused]] const long long pt0 = TIC_PROF_NOW();
     auto epilogue2 = [&](long long estep, int en, int ety, int etx) {
       const uint32_t b = (uint32_t)(estep & 1);
       TIC_PROF_WAIT(pw2, ptx::mbar_wait(&bars->acc2_full[b], (uint32_t)((estep >> 1) & 1)));
@@ -407,7 +407,7 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     if (step > 0) epilogue2(step - 1, pn, pty, ptx_);
     if (ovf_hit(omax)) ovf_raise(a1.oflow);
     if (warp == 4 || warp == 8) {
-      const int base = warp == 4 ? 16 : 24;
+      [[maybe_unused]] const int base = warp == 4 ? 16 : 24;
       TIC_PROF_ADD(base + 0, pw0);
       TIC_PROF_ADD(base + 1, pw1);
       TIC_PROF_ADD(base + 2, pw2);

@@ -210,8 +210,8 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
       const uint32_t w2A_d = (ptx::smem_u32(s_w2A) >> 4) | (1u << 16), w2B_d = (ptx::smem_u32(s_w2B) >> 4) | (1u << 16);
       const uint32_t reg_d = (ptx::smem_u32(s_region) >> 4) | (1u << 16);
       ptx::mbar_wait(&bars->w_full, 0);
-      long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
-      const long long pt0 = TIC_PROF_NOW();
+      [[maybe_unused]] long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0;
+      [[maybe_unused]] const long long pt0 = TIC_PROF_NOW();
       auto mma1 = [&](long long step) {
         TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_empty, (uint32_t)(step & 1) ^ 1u));
         TIC_PROF_WAIT(pw1, ptx::mbar_wait(&bars->op_full, (uint32_t)(step & 1)));
@@ -280,8 +280,8 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     const float std0 = a1.stdv[0], std1 = a1.stdv[1], std2 = a1.stdv[2];
     const float rstd0 = __frcp_rn(std0), rstd1 = __frcp_rn(std1), rstd2 = __frcp_rn(std2);
     long long step = 0;
-    long long pw0 = 0, pw1 = 0;
-    const long long pt0 = TIC_PROF_NOW();
+    [[maybe_unused]] long long pw0 = 0, pw1 = 0;
+    [[maybe_unused]] const long long pt0 = TIC_PROF_NOW();
     // byte k of `w` as a float (exact): 0x4B0000bb is 8388608 + bb
     auto byte_f = [](const uint32_t w, const uint32_t k) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | k)), 8388608.0f); };
     auto build = [&](const int item, const uint32_t w0, const uint32_t w1, const int ty, const int tx) {
@@ -369,8 +369,8 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     auto cell = [](int r, int c) { return (uint32_t)((((r >> 1) * 2 + (r & 1)) * 9 + (c >> 1)) * 128 + (c & 1) * 64); };
     const uint32_t pix = cell(R, C);
     __half2 omax = __floats2half2_rn(0.f, 0.f);
-    long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0, pw5 = 0, pw6 = 0, pw7 = 0, pw8 = 0;
-    const long long pt0 = TIC_PROF_NOW();
+    [[maybe_unused]] long long pw0 = 0, pw1 = 0, pw2 = 0, pw3 = 0, pw4 = 0, pw5 = 0, pw6 = 0, pw7 = 0, pw8 = 0;
+    [[maybe_unused]] const long long pt0 = TIC_PROF_NOW();
     // epilogue 2, one tile behind, shared by all sixteen warps (on the four warps of sub-tile 0 alone it took 2400 cycles
     // of a 6100-cycle step and everything else waited for them): the four warps of a TMEM lane quadrant take eight of
     // encode_1's 32 channels each — one 16-byte chunk per pixel and plane of the quadrant's TMA-store image
@@ -438,7 +438,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
         // one warp polls, the rest parks in a named barrier (every polling warp costs issue slots)
         if (warp == 8) TIC_PROF_WAIT(pw0, ptx::mbar_wait(&bars->acc1_full, (uint32_t)(step & 1)));
         TIC_PROF_WAIT(pw5, asm volatile("bar.sync 3, 512;" ::: "memory"));
-        const long long pta = TIC_PROF_NOW();
+        [[maybe_unused]] const long long pta = TIC_PROF_NOW();
         ptx::tc_fence_after();
         uint32_t hp[2][8], lp[2][8];
 #pragma unroll
@@ -468,7 +468,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
         if (sub == 0 && lane == 0) ptx::bulk_wait_group_read<0>();   // this quadrant's previous TMA store has read the stage
         // region free; the previous tile's cache writes are visible; the stage may be rewritten in phase C
         TIC_PROF_WAIT(pw4, asm volatile("bar.sync 2, 512;" ::: "memory"));
-        const long long ptb = TIC_PROF_NOW();
+        [[maybe_unused]] const long long ptb = TIC_PROF_NOW();
         // halo: row 32 (17 pixels, corner last) and column 16 (32 pixels) of the region, 8 chunks of 16 B each
         if (e < 49 * 8 && !(TIC_DBG_BITS(p2.dbg) & 4)) {
           const int hx = e >> 3, ch = e & 7;              // ch 0..3: hi plane, 4..7: lo' plane
@@ -529,7 +529,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     if (sub == 0 && lane == 0) ptx::bulk_wait_group<0>();   // every TMA store of this warp is complete before the CTA may exit
     if (ovf_hit(omax)) ovf_raise(a1.oflow);
     if (warp == 4 || warp == 8) {   // an epilogue-2 warp and a plain one
-      const int base = warp == 4 ? 16 : 24;
+      [[maybe_unused]] const int base = warp == 4 ? 16 : 24;
       TIC_PROF_ADD(base + 0, pw0);
       TIC_PROF_ADD(base + 1, pw1);
       TIC_PROF_ADD(base + 2, pw2);
@@ -541,7 +541,6 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
       TIC_PROF_ADD(base + 18, pw7);
       TIC_PROF_ADD(base + 19, pw8);
     }
-    (void)pw5; (void)pw6; (void)pw7; (void)pw8;
   }
 
   ptx::tc_fence_before();

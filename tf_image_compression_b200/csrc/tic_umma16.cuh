@@ -312,7 +312,7 @@ __device__ __forceinline__ void split16x2(float v0, float v1, uint32_t& hp, uint
 // Epilogue of one tile for one epilogue warp: TMEM lane = tile row = pixel (n, yt, xt); the warp takes
 // every other 16-column chunk (`half`).  Adds bias, activation, residual, and stores pair planes | f32 |
 // symbols (+ histogram) | the denormalised, clipped, rounded image (3-channel last layer).
-template <int MODE>
+template <int MODE, int NP = 2>   // NP = epilogue warps per TMEM lane quadrant: `half` in [0, NP) picks every NP-th chunk
 __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int NPAD, const int oc0, const int nsplit,
                                                   const uint32_t tbuf, const int n, const int yt, const int xt, const bool valid,
                                                   const int half, const float* s_bias, unsigned* s_hist, int& h_ones,
@@ -438,13 +438,13 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
       return tbuf + (u16_is_ph(MODE) ? (uint32_t)(ph * cpad) : (uint32_t)ph * 2u * NPAD) + c;
     };
     if (kDeconv || nsplit == 1) {
-      for (int u = half; u < U; u += 4) {
+      for (int u = half; u < U; u += 2 * NP) {
         int cA, pA, cB = 0, pB = 0;
         const uint32_t tA = unit_t(u, cA, pA);
-        const bool hasB = u + 2 < U;
+        const bool hasB = u + NP < U;
         float va[16], la[16];
         if (hasB) {
-          const uint32_t tB = unit_t(u + 2, cB, pB);
+          const uint32_t tB = unit_t(u + NP, cB, pB);
           float vb[16], lb[16];
           ptx::tmem_ld16_nowait(tA + NPAD, la);
           ptx::tmem_ld16_nowait(tA, va);
@@ -472,7 +472,7 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
         }
       }
     } else {
-      for (int c = half * 16; c < cend; c += 32) {
+      for (int c = half * 16; c < cend; c += 16 * NP) {
         float v[16];
         u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, 0, c, cpad);
         if (valid) finish(v, c, 0);
@@ -483,7 +483,7 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
   for (int ph = 0; ph < phases; ++ph) {
     const int y = kDeconv ? 2 * yt + (ph >> 1) : yt;
     const int x = kDeconv ? 2 * xt + (ph & 1) : xt;
-    for (int c = half * 16; c < cend; c += 32) {
+    for (int c = half * 16; c < cend; c += 16 * NP) {
       float v[16];
       u16_load_chunk<MODE>(v, tbuf, NPAD, nsplit, ph, c, cpad);
       const int cl = c;          // channel inside the slice
@@ -962,8 +962,11 @@ u16_conv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 // committed to both CTAs (multicast); `acc_empty` lives in the leader and collects both epilogues.
 // PPS = planes per ring slot (compile-time: the issuing warp's instruction stream bounds the layers with small N, and
 // any run-time structure in it — loops, branches, calls — measured 5-25 % slower on those layers).
-template <int MODE, int PPS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kU16Threads, 1)
+// EW = epilogue warps (8 | 16): four per TMEM lane quadrant for the quantiser layer, whose per-element sigmoid makes the
+// epilogue the tile time (see u16_launch_pair_pps for what was measured on the other layers).  The staged epilogue (a warp
+// group per TMEM buffer) and the 3-channel image epilogue need eight.
+template <int MODE, int PPS, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * EW, 1)
 u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, const U16Params p,
                 const LayerArgs a) {
   const int NPAD = p.npad;
@@ -990,7 +993,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&bars->acc_full[i], 1);
-      ptx::mbar_init(&bars->acc_empty[i], p.staged ? 8 : 16);  // epilogue warps of both CTAs (leader's copy is the live one)
+      ptx::mbar_init(&bars->acc_empty[i], p.staged ? 8 : 2 * EW);  // epilogue warps of both CTAs (leader's copy is the live one)
     }
     ptx::fence_barrier_init();
   }
@@ -998,7 +1001,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     ptx::tmem_alloc2(&bars->tmem_base, 512);
     ptx::tmem_relinquish2();
   }
-  for (int i = tid; i < 256; i += kU16Threads) s_hist[i] = 0;
+  for (int i = tid; i < 256; i += 128 + 32 * EW) s_hist[i] = 0;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync();  // the peer's barriers exist before anything remote touches them
@@ -1130,7 +1133,7 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     __half2 omax = __floats2half2_rn(0.f, 0.f);
     uint32_t ti = 0;
     for (long long tp = pair0; tp < num_pairs; tp += npairs, ++ti) {
-      if (p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
+      if (EW == 8 && p.staged && (int)(ti & 1u) != half) continue;  // staged: a warp group owns every other tile (= one TMEM buffer)
       const uint32_t b = ti & ((uint32_t)p.nbuf - 1u);
       const uint32_t use = ti >> p.nbshift;
       ptx::mbar_wait(&bars->acc_full[b], use & 1);
@@ -1144,12 +1147,12 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const bool valid = n < p.n;
       const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16) + b * p.acc_cols;
       if (TIC_DBG_BITS(p.dbg) & 4) {
-      } else if (p.staged) {
+      } else if (EW == 8 && p.staged) {
         u16_epilogue_tile_staged<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, s_bias,
                                        s_stage + (size_t)(warp - 4) * kU16StagePerWarp, lane, p.cpad, &bars->acc_empty[b], 2, omax);
         continue;  // the staged epilogue released the buffer itself
       } else
-        u16_epilogue_tile<MODE>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, omax, p.cpad);
+        u16_epilogue_tile<MODE, EW / 4>(a, NPAD, p.oc0, p.nsplit, tbuf, n, yt, xt, valid, half, s_bias, s_hist, h_ones, h_valid, omax, p.cpad);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_leader(&bars->acc_empty[b]);
@@ -1164,8 +1167,8 @@ u16_pair_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           if (h_valid - h_ones) atomicAdd(&s_hist[0], (unsigned)(h_valid - h_ones));
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int i = tid - 128; i < a.q; i += 256)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EW) : "memory");
+      for (int i = tid - 128; i < a.q; i += 32 * EW)
         if (s_hist[i]) atomicAdd(&a.hist[i], (unsigned long long)s_hist[i]);
     }
   }
@@ -1213,17 +1216,27 @@ inline cudaError_t u16_launch_t(cudaStream_t stream, const CUtensorMap& th, cons
   return cudaGetLastError();
 }
 
-template <int MODE, int PPS>
-inline cudaError_t u16_launch_pair_pps(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
-                                       const LayerArgs& a, int grid, size_t smem) {
-  auto k = u16_pair_kernel<MODE, PPS>;
+template <int MODE, int PPS, int EW>
+inline cudaError_t u16_launch_pair_ew(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
+                                      const LayerArgs& a, int grid, size_t smem) {
+  auto k = u16_pair_kernel<MODE, PPS, EW>;
   static SmemAttrCache cache;
   {
     cudaError_t e = cache.ensure(reinterpret_cast<const void*>(k), smem);
     if (e != cudaSuccess) return e;
   }
-  k<<<grid, kU16Threads, smem, stream>>>(th, tl, p, a);  // __cluster_dims__(2, 1, 1): grid is even
+  k<<<grid, 128 + 32 * EW, smem, stream>>>(th, tl, p, a);  // __cluster_dims__(2, 1, 1): grid is even
   return cudaGetLastError();
+}
+template <int MODE, int PPS>
+inline cudaError_t u16_launch_pair_pps(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,
+                                       const LayerArgs& a, int grid, size_t smem) {
+  // sixteen epilogue warps only for the quantiser layer (sigmoid + symbol + histogram per element: encode_4 0.23 -> 0.17 ms).
+  // Measured on every other un-staged layer: slower (8x8x64 convs 0.14 -> 0.18 ms, encode_2 0.43 -> 0.59, decode_3 0.41 ->
+  // 0.44): the 96-register cap of 640 threads and the extra warps cost the issuing warp more than the epilogue gains.
+  if (MODE == U16_S1 && !p.staged && (a.out_mode == IO_QUANT_U8 || a.out_mode == IO_QUANT_F32))
+    return u16_launch_pair_ew<MODE, PPS, MODE == U16_S1 ? 16 : 8>(stream, th, tl, p, a, grid, smem);
+  return u16_launch_pair_ew<MODE, PPS, 8>(stream, th, tl, p, a, grid, smem);
 }
 template <int MODE>
 inline cudaError_t u16_launch_pair_t(cudaStream_t stream, const CUtensorMap& th, const CUtensorMap& tl, const U16Params& p,

@@ -50,6 +50,7 @@ struct FusedEncParams {
   uint32_t w1_off, w2_off, w2B_off, op_off, raw_off, region_off, rowc_off, colc_off, stage_off, bars_off;
   uint32_t smem_bytes;
   float bias1[32];          // encode_0's bias as launch constants (constant-bank operands: no shared-memory loads in phase A)
+  int moff[3];              // m_c = round(mean_c): the builders' exact integer operand is x - m_c (FusedEncNorm)
 };
 
 struct FusedEncBars {
@@ -64,28 +65,41 @@ struct FusedEncBars {
 
 __device__ __forceinline__ uint32_t fused_swz128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
 
+// The first layer reads u8 pixels, and (x - mean) / std of an integer is not needed as an fp16 PAIR: with m_c = round(mean_c)
+// the operand A = x - m_c is an integer of magnitude <= 255, EXACT in one fp16, and
+//     sum_c ((x_c - mean_c) / std_c) * W_c  =  sum_c (x_c - m_c) * (W_c / std_c)  +  1 * sum_c (m_c - mean_c) * (W_c / std_c).
+// The RGB0 quad's spare fourth channel carries the 1 (0 outside the patch, like the pixel itself: the conv's zero padding
+// stays exact at the patch border), W' = W / std and the correction row are split into (hi, lo') as before, and the A_lo' x
+// W_hi product of the pair scheme disappears: MMA1 is 12 instead of 24 instructions per step, the builders write one plane.
+struct FusedEncNorm {
+  float mean[3], stdv[3];
+  int m[3];
+};
+
 // device [9][3][32] fp32 -> per CTA rank r of the pair, per filter row kh:
-//   region A [k group (2)][32 rows][8 halves]: r = 0 -> W_hi rows, r = 1 -> W_lo' rows   (stacked product, N = 64 over the pair)
-//   region B [k group (2)][16 rows][8 halves]: W_hi rows r * 16 ...                        (A_lo' x W_hi, N = 32 over the pair)
-// k = px * 4 + c (RGB0 quads of 4 consecutive input pixels; the 4th pixel and the 4th channel are zero).
-// Layout per rank: A(kh = 0..2) 3 x 1024 B, then B(kh = 0..2) 3 x 512 B.
-__global__ void f16_build_weights_s2_pair_kernel(const float* __restrict__ w, int cout, uint8_t* __restrict__ img) {
-  const int per_rank = 3 * (2 * 32 * 8 + 2 * 16 * 8);  // halves
+//   [k group (2)][32 rows][8 halves]: r = 0 -> W'_hi rows, r = 1 -> W'_lo' rows   (stacked product, N = 64 over the pair)
+// k = px * 4 + c (RGB1 quads of 4 consecutive input pixels; the 4th pixel has zero weights).  Per rank: 3 x 1024 B.
+__global__ void f16_build_weights_s2_pair_kernel(const float* __restrict__ w, int cout, uint8_t* __restrict__ img, const FusedEncNorm nm) {
+  const int per_rank = 3 * 2 * 32 * 8;  // halves
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * per_rank; i += gridDim.x * blockDim.x) {
     const int rank = i / per_rank;
-    int j = i - rank * per_rank;
-    const bool inB = j >= 3 * 2 * 32 * 8;
-    if (inB) j -= 3 * 2 * 32 * 8;
-    const int rows = inB ? 16 : 32;
-    const int e = j & 7, row = (j >> 3) % rows, kg = (j / (8 * rows)) & 1, kh = j / (16 * rows);
+    const int j = i - rank * per_rank;
+    const int e = j & 7, row = (j >> 3) & 31, kg = (j >> 8) & 1, kh = j >> 9;
     const int k = kg * 8 + e, px = k >> 2, c = k & 3;
-    const int oc = inB ? rank * 16 + row : row;
-    const float v = (px < 3 && c < 3 && oc < cout) ? w[((kh * 3 + px) * 3 + c) * cout + oc] : 0.f;
+    const int oc = row;
+    float v = 0.f;
+    if (px < 3 && oc < cout) {
+      const float* wt = w + (size_t)((kh * 3 + px) * 3) * cout + oc;   // [c][oc] of this tap
+      if (c < 3) {
+        v = __fdiv_rn(wt[c * cout], nm.stdv[c]);
+      } else {
+        for (int cc = 0; cc < 3; ++cc) v = __fmaf_rn(__fsub_rn((float)nm.m[cc], nm.mean[cc]), __fdiv_rn(wt[cc * cout], nm.stdv[cc]), v);
+      }
+    }
     __half hi, lo;
     split16(v, hi, lo);
-    const bool want_lo = !inB && rank == 1;
-    uint8_t* base = img + (size_t)rank * 4608 + (inB ? 3072 + kh * 512 : kh * 1024);
-    *reinterpret_cast<__half*>(base + (size_t)kg * (rows * 16) + (size_t)row * 16 + e * 2) = want_lo ? lo : hi;
+    uint8_t* base = img + (size_t)rank * 4608 + kh * 1024;
+    *reinterpret_cast<__half*>(base + (size_t)kg * 512 + (size_t)row * 16 + e * 2) = rank == 1 ? lo : hi;
   }
 }
 
@@ -98,7 +112,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
   uint8_t* s_w1 = smem + fp.w1_off;            // 4608 B: this rank's first-layer operand image
   uint8_t* s_w2A = smem + fp.w2_off;
   uint8_t* s_w2B = smem + fp.w2B_off;
-  uint8_t* s_op = smem + fp.op_off;            // hi plane | lo' plane of the normalised input window (RGB0 quads)
+  uint8_t* s_op = smem + fp.op_off;            // the input window as exact fp16 integers (x - m_c, 1): RGB1 quads, one plane
   uint8_t* s_rawwin = smem + fp.raw_off;
   uint8_t* s_region = smem + fp.region_off;    // hi plane | lo' plane of the 33 x 17 intermediate region (stride-2 box layout)
   uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][tiles_x][16 px][hi 64 B | lo 64 B]
@@ -195,12 +209,11 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     // ===== MMA issuer (leader): MMA1 of tile i + 1 is issued before MMA2 of tile i =====
     if (leader && nsteps > 0) {
       // first layer: un-swizzled K-major operands straight over the input window (tic_first16.cuh), M = 256 over the pair
-      const uint32_t idesc1_st = ptx::make_idesc_f16(256, 64), idesc1_lo = ptx::make_idesc_f16(256, 32);
+      const uint32_t idesc1_st = ptx::make_idesc_f16(256, 64);
       const uint32_t a1_hi32 = ((2u * kFEOpPitch) >> 4) | (1u << 14);
       const uint32_t w1_hi32 = (128u >> 4) | (1u << 14);
       const uint32_t a1_lbo = (16u >> 4) << 16;
       const uint32_t w1A_d = (ptx::smem_u32(s_w1) >> 4) | (((32u * 16u) >> 4) << 16);           // k-group stride: 32 rows x 16 B
-      const uint32_t w1B_d = (ptx::smem_u32(s_w1 + 3072) >> 4) | (((16u * 16u) >> 4) << 16);    // 16 rows x 16 B
       const uint32_t op_d = (ptx::smem_u32(s_op) >> 4) | a1_lbo;
       // second layer: the stride-2 pair kernel's operand geometry over the region buffer
       const uint32_t idesc2_st = ptx::make_idesc_f16(256, 2 * NPAD2), idesc2_lo = ptx::make_idesc_f16(256, NPAD2);
@@ -220,15 +233,12 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
 #pragma unroll
           for (int sub = 0; sub < 4; ++sub) {
             const uint32_t aoff = ((uint32_t)((sub >> 1) * 32) * kFEOpPitch + (uint32_t)((sub & 1) * 16) * 8u) >> 4;
-            const uint32_t ah = op_d + aoff, al = ah + (kFEOpPlane >> 4);
-            const uint32_t d = tmem_base + (uint32_t)sub * 64u;
+            const uint32_t ah = op_d + aoff;
+            const uint32_t d = tmem_base + (uint32_t)sub * 64u;   // columns 0-31: A x W'_hi, 32-63: A x W'_lo' (A is exact)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+            for (int kh = 0; kh < 3; ++kh)
               ptx::mma2_f16_ss(d, u16_desc(ah + (uint32_t)kh * (kFEOpPitch >> 4), a1_hi32), u16_desc(w1A_d + (uint32_t)kh * (1024u >> 4), w1_hi32),
                                idesc1_st, kh ? 1u : 0u);
-              ptx::mma2_f16_ss(d + 32u, u16_desc(al + (uint32_t)kh * (kFEOpPitch >> 4), a1_hi32), u16_desc(w1B_d + (uint32_t)kh * (512u >> 4), w1_hi32),
-                               idesc1_lo, 1u);
-            }
           }
         }
         __syncwarp();
@@ -268,43 +278,37 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
       TIC_PROF_ADD(5, nsteps);
     }
   } else if (warp >= kFEBuilderWarp0) {
-    // ===== builders: raw u8 window -> normalised (hi, lo') RGB0 quads of the 65 x 34-pixel input window =====
-    // The kernel sits on the shared-memory data pipe (ncu: LSU + tensor-core wavefronts = 92 % of its cycles), so the
-    // builders are written for wavefronts, not instructions: an item is (row, PAIR of pixels) — 65 x 17 = 1105 items,
+    // ===== builders: raw u8 window -> the exact integer operand (x - m_c, 1) as RGB1 fp16 quads of the 65 x 34 window =====
+    // The kernel sits on the shared-memory data pipe (ncu: LSU + tensor-core wavefronts = 92 % of its cycles before this
+    // layout), so the builders are written for wavefronts: an item is (row, PAIR of pixels) — 65 x 17 = 1105 items,
     // consecutive lanes take consecutive pairs.  Six raw bytes come from two aligned words (consecutive lanes: consecutive
-    // words), the normalisation (x - mean) / std is computed (f16_norm_fast: the correctly rounded quotient, same value as
-    // the 3 x 256 table of the stand-alone kernel whose twelve look-ups per quad cost a 3-way bank conflict each), and the
-    // two (hi, lo') quad pairs go out as one 16-byte store per plane at item * 16 — consecutive lanes, consecutive chunks.
+    // words); a byte b becomes the fp16 integer 1024 + b by byte permutation (0x6400 | b) and x - m_c by one exact half2
+    // subtraction (FusedEncNorm: no normalisation, no split, no table); the two quads go out as one 16-byte store at
+    // item * 16 — consecutive lanes, consecutive chunks.
     const int bl = (warp - kFEBuilderWarp0) * 32 + lane;
-    const float mean0 = a1.mean[0], mean1 = a1.mean[1], mean2 = a1.mean[2];
-    const float std0 = a1.stdv[0], std1 = a1.stdv[1], std2 = a1.stdv[2];
-    const float rstd0 = __frcp_rn(std0), rstd1 = __frcp_rn(std1), rstd2 = __frcp_rn(std2);
+    const __half2 c_rg = __floats2half2_rn(1024.0f + (float)fp.moff[0], 1024.0f + (float)fp.moff[1]);
+    const __half2 c_b1 = __floats2half2_rn(1024.0f + (float)fp.moff[2], 0.0f);
     long long step = 0;
     [[maybe_unused]] long long pw0 = 0, pw1 = 0;
     [[maybe_unused]] const long long pt0 = TIC_PROF_NOW();
-    // byte k of `w` as a float (exact): 0x4B0000bb is 8388608 + bb
-    auto byte_f = [](const uint32_t w, const uint32_t k) { return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | k)), 8388608.0f); };
+    auto as_h2 = [](const uint32_t x) { return *reinterpret_cast<const __half2*>(&x); };
+    auto as_u32 = [](const __half2 x) { return *reinterpret_cast<const uint32_t*>(&x); };
     auto build = [&](const int item, const uint32_t w0, const uint32_t w1, const int ty, const int tx) {
       const int ry = item / 17, pp = item - ry * 17;
       const uint32_t sh = (uint32_t)(pp & 1) * 16u;           // byte offset 6 * pp is 0 or 2 (mod 4)
-      const uint32_t lo32 = __funnelshift_r(w0, w1, sh);      // R0 G0 B0 R1
-      const uint32_t hi16 = w1 >> sh;                         // G1 B1
+      const uint32_t p0 = __funnelshift_r(w0, w1, sh);        // R0 G0 B0 R1
+      const uint32_t p1 = __byte_perm(p0, w1 >> sh, 0x5543);  // R1 G1 B1 .
       const bool row_ok = 64 * ty + ry < fp.P;
       const int ix = 32 * tx + 2 * pp;
       const bool ok0 = row_ok && ix < fp.P, ok1 = row_ok && ix + 1 < fp.P;
-      float r0 = f16_norm_fast(byte_f(lo32, 0), mean0, std0, rstd0), g0 = f16_norm_fast(byte_f(lo32, 1), mean1, std1, rstd1);
-      float b0 = f16_norm_fast(byte_f(lo32, 2), mean2, std2, rstd2), r1 = f16_norm_fast(byte_f(lo32, 3), mean0, std0, rstd0);
-      float g1 = f16_norm_fast(byte_f(hi16, 0), mean1, std1, rstd1), b1 = f16_norm_fast(byte_f(hi16, 1), mean2, std2, rstd2);
-      if (!ok0) r0 = g0 = b0 = 0.f;   // outside the patch: the conv's zero padding
-      if (!ok1) r1 = g1 = b1 = 0.f;
-      uint32_t h[4], l[4];
-      split16x2(r0, g0, h[0], l[0]);
-      split16x2(b0, 0.f, h[1], l[1]);
-      split16x2(r1, g1, h[2], l[2]);
-      split16x2(b1, 0.f, h[3], l[3]);
-      const uint32_t dst = ptx::smem_u32(s_op) + (uint32_t)item * 16u;   // row pitch 272 B = 17 pairs x 16 B
-      sts128(dst, h[0], h[1], h[2], h[3]);
-      sts128(dst + kFEOpPlane, l[0], l[1], l[2], l[3]);
+      // (1024 + R, 1024 + G) and (1024 + B, 1.0): bytes (b, 0x64, b', 0x64) and (b, 0x64, 0x00, 0x3C)
+      uint32_t q0 = as_u32(__hsub2(as_h2(__byte_perm(p0, 0x64646464u, 0x4140)), c_rg));
+      uint32_t q1 = as_u32(__hsub2(as_h2(__byte_perm(p0, 0x3C000064u, 0x7542)), c_b1));
+      uint32_t q2 = as_u32(__hsub2(as_h2(__byte_perm(p1, 0x64646464u, 0x4140)), c_rg));
+      uint32_t q3 = as_u32(__hsub2(as_h2(__byte_perm(p1, 0x3C000064u, 0x7542)), c_b1));
+      if (!ok0) q0 = q1 = 0u;   // outside the patch: the conv's zero padding (pixel and its constant 1)
+      if (!ok1) q2 = q3 = 0u;
+      sts128(ptx::smem_u32(s_op) + (uint32_t)item * 16u, q0, q1, q2, q3);   // row pitch 272 B = 17 pairs x 16 B
     };
     constexpr int kItems = kFEOpRows * 17, kLanes = kFEBuilders * 32;
     for (long long pp = pair0; pp < fp.pairs_total; pp += npairs) {
@@ -565,6 +569,7 @@ inline bool fused_enc_supported(const LayerArgs& a1, int kind1, int stride1, con
 
 struct FusedEncWeights {
   uint8_t* w1 = nullptr;
+  FusedEncNorm nm{};        // the normalisation constants folded into w1 (tic_set_norm after the first launch rebuilds it)
   U16WeightSlice w2;
   void release() {
     if (w1) cudaFree(w1);
@@ -588,9 +593,18 @@ inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const Laye
   U16Params p2 = pl2.p;
   if (p2.mode != U16_S2 || p2.nbox != 1 || p2.ksteps != 2 || p2.KB != 1 || p2.bn != 1 || p2.npad != 32 || p2.nsplit != 1)
     return fail("fused encoder: unexpected layer plan", -5);
-  if (!fw->w1) {
-    if (cudaMalloc(&fw->w1, 2 * 4608) != cudaSuccess) return fail("cudaMalloc for the fused first-layer weight image failed", -4);
-    f16_build_weights_s2_pair_kernel<<<8, 256, 0, stream>>>(w1_dev, a1.cout, fw->w1);
+  FusedEncNorm nm{};
+  for (int c = 0; c < 3; ++c) {
+    nm.mean[c] = a1.mean[c];
+    nm.stdv[c] = a1.stdv[c];
+    nm.m[c] = (int)lrintf(a1.mean[c]);
+    if (nm.m[c] < -768 || nm.m[c] > 1023) return fail("fused encoder: channel mean outside the exact fp16 integer range", -5);
+  }
+  if (!fw->w1 || memcmp(&fw->nm, &nm, sizeof(nm)) != 0) {
+    // (a rebuild on the same stream is ordered behind the launches that still read the old image)
+    if (!fw->w1 && cudaMalloc(&fw->w1, 2 * 4608) != cudaSuccess) return fail("cudaMalloc for the fused first-layer weight image failed", -4);
+    fw->nm = nm;
+    f16_build_weights_s2_pair_kernel<<<8, 256, 0, stream>>>(w1_dev, a1.cout, fw->w1, nm);
     if (cudaGetLastError() != cudaSuccess) return fail("fused first-layer weight image kernel failed", -2);
   }
   if (u16_ensure_pair_weights(stream, w2_dev, a2, p2, &fw->w2) != 0) return fail("fused encoder: weight images failed", -2);
@@ -605,6 +619,7 @@ inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const Laye
   fp.tiles_pp = fp.tiles_x * fp.tiles_y;
   fp.pairs_total = ((long long)a1.n + 1) / 2;
   fp.w1img = fw->w1;
+  for (int c = 0; c < 3; ++c) fp.moff[c] = nm.m[c];
   for (int i = 0; i < 32; ++i) fp.bias1[i] = i < a1.cout ? bias1_host[i] : 0.f;
   auto up = [](uint32_t v) { return (v + 1023u) & ~1023u; };
   uint32_t off = 0;
@@ -615,7 +630,7 @@ inline int launch_fused_enc(cudaStream_t stream, const LayerArgs& a1, const Laye
   fp.w2B_off = off;
   off += up(p2.wB_bytes);
   fp.op_off = off;
-  off += up(2u * kFEOpPlane);
+  off += up(kFEOpPlane);
   fp.raw_off = off;
   off += up(kFERawStages * kFERawStage);
   fp.region_off = off;

@@ -452,7 +452,7 @@ int run_graph(tic_codec* h, int gi, const IoSpec& io_in, const IoSpec& io_out, i
                                                              hi + count, count, h->d_oflow);
         else
           u16_split_symlut_kernel<<<blocks, 256, 0, h->stream>>>(
-              reinterpret_cast<const uint8_t*>(io_in.in) + ((long long)io_in.geo.n0 + s0) * per, h->d_symlut, hi, hi + count, count,
+              reinterpret_cast<const uint8_t*>(io_in.in) + ((long long)io_in.geo.n0 + s0) * per, h->d_symlut, h->q, hi, hi + count, count,
               h->d_oflow);
         h->launches++;
         TIC_CUDA(h, cudaGetLastError());

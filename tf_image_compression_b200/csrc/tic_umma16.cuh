@@ -586,12 +586,12 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
 constexpr uint32_t kU16StagePerWarp = 4096;
 constexpr uint32_t kU16StageBytes = 8 * kU16StagePerWarp;
 
-__host__ __device__ inline bool u16_staged_ok(const LayerArgs& a, int mode, int nbuf, int cend) {
+__host__ __device__ inline bool u16_staged_ok(const LayerArgs& a, int mode, int nbuf, int cend, bool slices_ok = false) {
   if (nbuf < 2 || a.out_mode != IO_ACT16 || (a.cout & 15) != 0) return false;
   if (mode == U16_DECONV) return false;                       // tap-based 64-channel deconv: one TMEM buffer
   // 64-channel layers sit on 8x8 / 16x16 maps at the HBM roofline already and need the 32 KB for operand slots
   if (!(cend == 16 || cend == 32)) return false;
-  if (cend != a.cout) return false;                           // output-channel slices: the row is not owned by one launch
+  if (cend != a.cout && !slices_ok) return false;             // output-channel slices: the row is not owned by one launch
   return true;
 }
 
@@ -1399,7 +1399,8 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   p.nbshift = p.nbuf == 4 ? 2 : (p.nbuf == 2 ? 1 : 0);
   p.dbg = tic_env_int("TIC_DBG", 0);  // -DTIC_ABLATE builds only
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
-  p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad) ? 1 : 0;
+  // (phase-stacked output-channel slices keep the staged epilogue: a slice owns 64 contiguous bytes of every pixel row)
+  p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad, p.mode == U16_DECONV_PH) ? 1 : 0;
   const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
   const size_t wres = ((p.w_bytes + 1023u) & ~1023u) + (p.staged ? kU16StageBytes : 0u);
   if (wres + 2 * (size_t)p.slot_bytes > budget) return false;
@@ -1424,8 +1425,10 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
   const bool pair = pair_enabled && num_sms >= 2;
   U16Plan plan{};
   int cs = std::min(a.cout, 128);
-  // (64-channel transposed conv as two phase-stacked 32-channel slices measured slower than tap-based: 0.51 vs 0.43 ms)
-  if (kind == 1 && tic_env_set("TIC_DECONV_PH_SLICES")) cs = std::min(cs, 32);
+  // Transposed convs with 64 or more output channels run as phase-stacked 32-channel slices WITH the staged epilogue:
+  // decode_3 (64 -> 64 on 8 x 8 maps) 0.42 ms tap-based (one TMEM buffer, epilogue-bound on 16-byte strided stores), 0.37 ms
+  // as slices with the direct epilogue, 0.28 ms as slices with the staged one; the input (small) is read once per slice.
+  if (kind == 1 && a.cout >= 64 && a.cout % 32 == 0 && tic_env_int("TIC_DECONV_TAP", 0) == 0) cs = std::min(cs, 32);
   // (ablation builds) tap-based slices of 32 output channels: two TMEM buffers instead of one (the unsliced 64-channel
   // tile needs all 512 columns, so its MMAs and its epilogue alternate).  Measured on decode_3: 2 x 0.205 ms against
   // 0.414 ms unsliced, identical output — the layer is bound by its epilogue's 16-byte strided stores, not by the

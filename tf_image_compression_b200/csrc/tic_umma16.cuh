@@ -586,11 +586,12 @@ __device__ __forceinline__ void u16_epilogue_tile(const LayerArgs& a, const int 
 constexpr uint32_t kU16StagePerWarp = 4096;
 constexpr uint32_t kU16StageBytes = 8 * kU16StagePerWarp;
 
-__host__ __device__ inline bool u16_staged_ok(const LayerArgs& a, int mode, int nbuf, int cend, bool slices_ok = false) {
+__host__ __device__ inline bool u16_staged_ok(const LayerArgs& a, int mode, int nbuf, int cend, bool slices_ok = false, bool allow64 = false) {
   if (nbuf < 2 || a.out_mode != IO_ACT16 || (a.cout & 15) != 0) return false;
   if (mode == U16_DECONV) return false;                       // tap-based 64-channel deconv: one TMEM buffer
-  // 64-channel layers sit on 8x8 / 16x16 maps at the HBM roofline already and need the 32 KB for operand slots
-  if (!(cend == 16 || cend == 32)) return false;
+  // 64-channel conv layers: 32 pixels x 128 B is exactly a warp's 4 KB stage (measured: encode_2 0.47 -> 0.38 ms, the
+  // residual layers 0.21 -> 0.19 ms, the plain 8x8x64 layers 0.145 -> 0.14 ms, same output)
+  if (!(cend == 16 || cend == 32 || (cend == 64 && (mode == U16_S1 || mode == U16_S2) && allow64))) return false;
   if (cend != a.cout && !slices_ok) return false;             // output-channel slices: the row is not owned by one launch
   return true;
 }
@@ -754,6 +755,9 @@ __device__ __forceinline__ void u16_epilogue_tile_staged(const LayerArgs& a, con
     u16_epilogue_tile_staged_t<MODE, 32>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind, omax);
   else if (cend == 16)
     u16_epilogue_tile_staged_t<MODE, 16>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane, cpad, rel_bar, rel_kind, omax);
+  else if (cend == 64 && !u16_is_ph(MODE) && MODE != U16_DECONV)   // 32 pixels x 128 B = the warp's 4 KB stage
+    u16_epilogue_tile_staged_t<(u16_is_ph(MODE) || MODE == U16_DECONV) ? U16_S1 : MODE, 64>(a, NPAD, oc0, nsplit, tbuf, n, yt, xt, valid, s_bias, st, lane,
+                                                                                          cpad, rel_bar, rel_kind, omax);
 }
 
 // KS = MMAs (K = 16) per tap and K-block, compile-time: with a run-time bound the unrolled body carries four
@@ -1400,7 +1404,8 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   p.dbg = tic_env_int("TIC_DBG", 0);  // -DTIC_ABLATE builds only
   if (2 * p.npad > 256) return false;  // MMA N limit for the stacked product
   // (phase-stacked output-channel slices keep the staged epilogue: a slice owns 64 contiguous bytes of every pixel row)
-  p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad, p.mode == U16_DECONV_PH) ? 1 : 0;
+  p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad, p.mode == U16_DECONV_PH,
+                           tic_env_int("TIC_STAGED64", 1) != 0) ? 1 : 0;   // knob: -DTIC_ABLATE builds only
   const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
   const size_t wres = ((p.w_bytes + 1023u) & ~1023u) + (p.staged ? kU16StageBytes : 0u);
   if (wres + 2 * (size_t)p.slot_bytes > budget) return false;

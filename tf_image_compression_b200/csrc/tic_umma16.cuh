@@ -1282,12 +1282,15 @@ inline cudaError_t u16_launch_pair_t(cudaStream_t stream, const CUtensorMap& th,
 
 struct U16Plan {
   int cs;      // output channels per slice
+  int variant; // u16_plan's variant bits
   U16Params p;
   size_t smem;
 };
 
 // Geometry + shared-memory plan for one slice width; returns false if it does not fit.
-inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out, bool pair = false, bool allow_ph = true) {
+// variant: bit 0 = 32-channel K-blocks (half-size operand slots), bit 1 = no staged epilogue (its 32 KB go to the ring)
+inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* out, bool pair = false, bool allow_ph = true,
+                     int variant = 0) {
   U16Params p{};
   p.pair = pair ? 1 : 0;
   p.mode = u16_mode_of(kind, stride);
@@ -1302,7 +1305,7 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   if (p.num_tiles >= (1LL << 31) - 65536) return false;  // FastDiv range (and the 32-bit tile counters)
   p.tx_d = make_fastdiv((uint32_t)p.tiles_x);
   p.ty_d = make_fastdiv((uint32_t)p.tiles_y);
-  p.kc = std::min(a.cin, 64);
+  p.kc = std::min(a.cin, (variant & 1) ? 32 : 64);
   p.KB = a.cin / p.kc;
   p.ksteps = p.kc / 16;
   p.npad = (cs + 15) / 16 * 16;
@@ -1406,12 +1409,14 @@ inline bool u16_plan(const LayerArgs& a, int kind, int stride, int cs, U16Plan* 
   // (phase-stacked output-channel slices keep the staged epilogue: a slice owns 64 contiguous bytes of every pixel row)
   p.staged = u16_staged_ok(a, p.mode, p.nbuf, p.mode == U16_DECONV_PH ? p.cpad : p.npad, p.mode == U16_DECONV_PH,
                            tic_env_int("TIC_STAGED64", 1) != 0) ? 1 : 0;   // knob: -DTIC_ABLATE builds only
+  if (variant & 2) p.staged = 0;
   const size_t budget = 227 * 1024 - 2048 /* static histogram + bias */ - 1024 /* alignment slack */ - sizeof(U16SmemBars) - 256;
   const size_t wres = ((p.w_bytes + 1023u) & ~1023u) + (p.staged ? kU16StageBytes : 0u);
   if (wres + 2 * (size_t)p.slot_bytes > budget) return false;
   p.S = (int)std::min<size_t>(kU16MaxSlots, (budget - wres) / p.slot_bytes);
   if (pair && p.S >= 4) p.S &= ~1;  // the pair kernel's ring slots hold both planes when four plane buffers fit
   out->cs = cs;
+  out->variant = variant;
   out->p = p;
   out->smem = wres + (size_t)p.S * p.slot_bytes + sizeof(U16SmemBars) + 1024;
   return true;
@@ -1442,8 +1447,16 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
   if (tap_slices) cs = std::min(cs, 32);
   cs = (cs + 15) / 16 * 16;
   bool ok = false;
-  for (; cs >= 16; cs -= 16)
-    if ((ok = u16_plan(a, kind, stride, std::min(cs, a.cout), &plan, pair, !tap_slices))) break;
+  // A stride-2 conv with 64 input channels whose full-width plan does not fit (two 83 KB parity boxes per plane next to
+  // 110 KB of weights) is tried with 32-channel K-blocks before its output channels are sliced: the slices each re-read
+  // the input (encode_3: 2 x 0.145 ms at 6.2 TB/s).
+  const bool small_kc = kind == 0 && stride == 2 && a.cin == 64 && tic_env_int("TIC_SMALL_KC", 1) != 0;  // knob: -DTIC_ABLATE builds only
+  for (; cs >= 16; cs -= 16) {
+    const int csl = std::min(cs, a.cout);
+    ok = u16_plan(a, kind, stride, csl, &plan, pair, !tap_slices);
+    if (!ok && small_kc) ok = u16_plan(a, kind, stride, csl, &plan, pair, !tap_slices, 1) || u16_plan(a, kind, stride, csl, &plan, pair, !tap_slices, 3);
+    if (ok) break;
+  }
   if (!ok) return fail("layer does not fit the fp16-pair tensor path", -5);
   cs = plan.cs;
 
@@ -1480,7 +1493,7 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
     if (si >= 16) return fail("too many output-channel slices", -5);
     const int csl = std::min(cs, a.cout - oc0);
     U16Plan pl{};
-    if (!u16_plan(a, kind, stride, csl, &pl, pair, !tap_slices)) return fail("slice plan failed", -5);
+    if (!u16_plan(a, kind, stride, csl, &pl, pair, !tap_slices, plan.variant)) return fail("slice plan failed", -5);
     U16Params p = pl.p;
     p.oc0 = oc0;
     U16WeightSlice* ws = &uw->slice[si];

@@ -1450,7 +1450,8 @@ inline int launch_u16(cudaStream_t stream, const LayerArgs& a, int kind, int str
   // A stride-2 conv with 64 input channels whose full-width plan does not fit (two 83 KB parity boxes per plane next to
   // 110 KB of weights) is tried with 32-channel K-blocks before its output channels are sliced: the slices each re-read
   // the input (encode_3: 2 x 0.145 ms at 6.2 TB/s).
-  const bool small_kc = kind == 0 && stride == 2 && a.cin == 64 && tic_env_int("TIC_SMALL_KC", 1) != 0;  // knob: -DTIC_ABLATE builds only
+  const int small_kc_knob = tic_env_int("TIC_SMALL_KC", 1);  // knob: -DTIC_ABLATE builds only (2: any conv with >= 64 input channels)
+  const bool small_kc = (kind == 0 && stride == 2 && a.cin == 64 && small_kc_knob != 0) || (kind == 0 && a.cin >= 64 && small_kc_knob == 2);
   for (; cs >= 16; cs -= 16) {
     const int csl = std::min(cs, a.cout);
     ok = u16_plan(a, kind, stride, csl, &plan, pair, !tap_slices);

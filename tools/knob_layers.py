@@ -16,13 +16,15 @@ assert _L.LIB_PATH.exists(), "run tools/build_ablate.sh first"
 which, knob, values = sys.argv[1], sys.argv[2], sys.argv[3:]
 mean = np.array([118.3, 113.9, 102.6], np.float32)
 std = np.array([61.7, 59.2, 63.8], np.float32)
-codec = T.Codec("model_0", quan_scale=2, mean=mean, std=std, compute="tensor")
+VARIANT = os.environ.get("VARIANT", "model_0")
+codec = T.Codec(VARIANT, quan_scale=2, mean=mean, std=std, compute="tensor")
 codec.use_torch_stream()
-n, H, W, P = 64, 1536, 2048, 128
+n, H, W, P = int(os.environ.get("NIMG", "64")), 1536, 2048, 128
+hb, wb, cb = codec.bottleneck_shape(P)
 img = torch.randint(0, 256, (n, H, W, 3), dtype=torch.uint8, device="cuda")
-sym = torch.randint(0, 2, (n, 192, 8, 8, 64), dtype=torch.uint8, device="cuda")
+sym = torch.randint(0, 2, (n, 192, hb, wb, cb), dtype=torch.uint8, device="cuda")
 rec = torch.empty((n, H, W, 3), dtype=torch.uint8, device="cuda")
-osym = torch.empty((n, 192, 8, 8, 64), dtype=torch.uint8, device="cuda")
+osym = torch.empty((n, 192, hb, wb, cb), dtype=torch.uint8, device="cuda")
 ref = None
 for v in values:
     os.environ[knob] = v

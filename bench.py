@@ -287,6 +287,9 @@ def roofline_of(rows, compute, variant, patch):
         per = td.get(variant, {}).get(f"{top['graph']}/{top['scope']}")
         if per is not None and patch == 128:
             traffic = per / td["patches_per_launch"] * top["npatch"] / top["launches"] if "npatch" in top else None
+        lim = td.get("limiters", {}).get(variant, {}).get(f"{top['graph']}/{top['scope']}")
+        if lim is not None and patch == 128:
+            rf["ncu_limiters"] = lim   # committed ncu evidence for what bounds this kernel when it is neither HBM nor tensor math
     rf.update({"traffic": traffic, "kernel": f"{top['graph']}/{top['scope']} ({compute})",
                "kernel_ms_per_launch": top_launch_s * 1e3, "kernel_share_of_step": top["ms_step"] / max(step_ms, 1e-9),
                "kernel_algorithmic_flop_per_byte": top["flops_step"] / top["bytes_step"], "ridge_flop_per_byte": ridge,

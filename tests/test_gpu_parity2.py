@@ -86,6 +86,25 @@ def test_fused_layer_pairs_on_edge_shapes(variant, P, h, w, nimg):
     codec.close()
 
 
+def test_tensor_path_launch_counts_guard_against_silent_fallbacks():
+    """model_0 at P = 128 on exact-grid u8 images, compute = tensor: 8 encoder launches (the fused first pair, encode_2,
+    encode_3 in ONE launch, four residual-block convs, encode_4) and 10 decoder launches (symbols -> pair planes, decode_4,
+    four convs, decode_3 as two phase-stacked slices, decode_2, the fused last pair).  A layer that silently dropped to
+    an un-fused or sliced plan shows up here before it shows up in the bench."""
+    codec, enc, dec = make_codec("model_0", "fanin", compute="tensor")
+    imgs = torch.from_numpy(np.stack([O.synthetic_image(256, 384, 80 + i) for i in range(4)])).cuda()
+    sym = codec.encode_images(imgs, 128)            # first call: lazily built weight images add launches
+    rec = codec.decode_images(sym, 256, 384, 128)
+    n0 = codec.launch_count
+    codec.encode_images(imgs, 128)
+    n1 = codec.launch_count
+    codec.decode_images(sym, 256, 384, 128)
+    n2 = codec.launch_count
+    assert (n1 - n0, n2 - n1) == (8, 10), (n1 - n0, n2 - n1)
+    assert tuple(rec.shape) == (4, 256, 384, 3)
+    codec.close()
+
+
 def test_fused_encoder_with_unusual_normalisation_constants():
     """The fused encoder folds 1 / std into the first layer's weights and works on the exact integers x - round(mean)
     (tic_fused_enc16.cuh, FusedEncNorm): identity normalisation, a mean of 0.5 (rounds to even), a tiny and a huge std, and

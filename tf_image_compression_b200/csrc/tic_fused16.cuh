@@ -126,8 +126,8 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
   uint8_t* s_w2B = smem + fp.w2B_off;
   uint8_t* s_in = smem + fp.in_off;            // 2 ring slots x (hi box | lo box)
   uint8_t* s_region = smem + fp.region_off;    // hi plane | lo plane
-  uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][tiles_x][16 px][hi 64 B | lo 64 B]
-  uint8_t* s_colc = smem + fp.colc_off;        // [parity][32 px][hi | lo]
+  uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][chunk: hi 0-3, lo' 4-7][tiles_x * 16 px][16 B]
+  uint8_t* s_colc = smem + fp.colc_off;        // [parity][chunk][32 px][16 B]
   FusedDecBars* bars = reinterpret_cast<FusedDecBars*>(smem + fp.bars_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -292,6 +292,7 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
     const uint32_t reg_hi = ptx::smem_u32(s_region), reg_lo = reg_hi + kFusedRegionLoOff;
     const uint32_t rowc = ptx::smem_u32(s_rowc), colc = ptx::smem_u32(s_colc);
     const uint32_t rowc_par = (uint32_t)fp.tiles_x * 16u * 128u;   // bytes of one parity of the row cache
+    const int rowc_px = fp.tiles_x * 16;                            // pixels of one cached row (chunk-major: [chunk 8][pixel][16 B])
     const uint32_t tbuf = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const float floor_v = a1.act ? 0.0f : -INFINITY;
     const int R = 2 * hh + py, C = 2 * xx + px;         // region coordinates of this lane's output pixel
@@ -350,14 +351,17 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
         TIC_PROF_WAIT(pw4, asm volatile("bar.sync 2, 512;" ::: "memory"));   // the previous tile's cache writes are visible to every epilogue-1 thread
         // halo: row -1 (17 pixels, corner first) and column -1 (32 pixels) of the region, 8 chunks of 16 B each
         if (e < 49 * 8 && !(TIC_DBG_BITS(p1.dbg) & 4)) {
-          const int hp_ix = e >> 3, ch = e & 7;           // ch 0..3: hi plane, 4..7: lo' plane
+          // consecutive lanes take consecutive halo pixels of one chunk: the caches are chunk-major ([chunk][pixel][16 B]),
+          // so their reads here and the row-cache writes below touch consecutive 16-byte units (pixel-major, the eight
+          // lanes that own a cached row wrote at a 128-byte stride: 8x the wavefronts)
+          const int ch = e / 49, hp_ix = e - ch * 49;     // ch 0..3: hi plane, 4..7: lo' plane
           uint4 val = make_uint4(0u, 0u, 0u, 0u);
           uint32_t dst_pix;
           if (hp_ix < 17) {                               // region row -1, column hp_ix - 1 (corner: the tile above-left)
-            if (ty > 0 && (hp_ix > 0 || tx > 0)) val = lds128(rowc_rd + (uint32_t)((tx * 16 + hp_ix - 1) * 128 + ch * 16));
+            if (ty > 0 && (hp_ix > 0 || tx > 0)) val = lds128(rowc_rd + (uint32_t)((ch * rowc_px + tx * 16 + hp_ix - 1) * 16));
             dst_pix = (uint32_t)hp_ix;
           } else {                                        // region column -1, row hp_ix - 17
-            if (tx > 0) val = lds128(colc_rd + (uint32_t)((hp_ix - 17) * 128 + ch * 16));
+            if (tx > 0) val = lds128(colc_rd + (uint32_t)((ch * 32 + hp_ix - 17) * 16));
             dst_pix = (uint32_t)((hp_ix - 17 + 1) * kFusedRegionCols);
           }
           const uint32_t addr = (ch < 4 ? reg_hi : reg_lo) + dst_pix * 64u + (uint32_t)(ch & 3) * 16u;
@@ -380,18 +384,18 @@ fused_dec_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constan
                    lo_first ? hp[ci][7] : lp[ci][7]);
           }
           if (R == 31) {   // last row of the region: halo row of the tile below (corner of the tile below-right)
-            const uint32_t c0 = rowc_wr + (uint32_t)((tx * 16 + C) * 128 + ci * 32);
+            const uint32_t c0 = rowc_wr + (uint32_t)((2 * ci * rowc_px + tx * 16 + C) * 16), cs = (uint32_t)rowc_px * 16u;
             sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
-            sts128(c0 + 16u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
-            sts128(c0 + 64u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
-            sts128(c0 + 80u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+            sts128(c0 + cs, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+            sts128(c0 + 4u * cs, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+            sts128(c0 + 5u * cs, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
           }
           if (C == 15) {   // last column: halo column of the tile to the right
-            const uint32_t c0 = colc_wr + (uint32_t)(R * 128 + ci * 32);
+            const uint32_t c0 = colc_wr + (uint32_t)((2 * ci * 32 + R) * 16);
             sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
-            sts128(c0 + 16u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
-            sts128(c0 + 64u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
-            sts128(c0 + 80u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+            sts128(c0 + 512u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+            sts128(c0 + 2048u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+            sts128(c0 + 2560u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
           }
         }
         ptx::fence_proxy_async_smem();   // generic-proxy region writes -> visible to the tensor core's operand reads

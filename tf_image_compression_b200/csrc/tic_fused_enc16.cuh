@@ -115,8 +115,8 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
   uint8_t* s_op = smem + fp.op_off;            // the input window as exact fp16 integers (x - m_c, 1): RGB1 quads, one plane
   uint8_t* s_rawwin = smem + fp.raw_off;
   uint8_t* s_region = smem + fp.region_off;    // hi plane | lo' plane of the 33 x 17 intermediate region (stride-2 box layout)
-  uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][tiles_x][16 px][hi 64 B | lo 64 B]
-  uint8_t* s_colc = smem + fp.colc_off;        // [parity][32 px][hi | lo]
+  uint8_t* s_rowc = smem + fp.rowc_off;        // [parity][chunk: hi 0-3, lo' 4-7][tiles_x * 16 px][16 B]
+  uint8_t* s_colc = smem + fp.colc_off;        // [parity][chunk][32 px][16 B]
   uint8_t* s_stage = smem + fp.stage_off;      // 4 x 4 KB: epilogue 2's TMA-store images (one per TMEM lane quadrant)
   FusedEncBars* bars = reinterpret_cast<FusedEncBars*>(smem + fp.bars_off);
   __shared__ __align__(16) float s_bias2[32];
@@ -365,6 +365,7 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
     const uint32_t reg_hi = ptx::smem_u32(s_region), reg_lo = reg_hi + kFERegionPlane;
     const uint32_t rowc = ptx::smem_u32(s_rowc), colc = ptx::smem_u32(s_colc);
     const uint32_t rowc_par = (uint32_t)fp.tiles_x * 16u * 128u;
+    const int rowc_px = fp.tiles_x * 16;   // pixels of one cached row (chunk-major caches: [chunk 8][pixel][16 B])
     const uint32_t tq = tmem_base + ((uint32_t)(q4 * 32) << 16);
     const uint32_t tbuf1 = tq + (uint32_t)sub * 64u;
     const float floor1 = a1.act ? 0.0f : -INFINITY;
@@ -475,14 +476,15 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
         [[maybe_unused]] const long long ptb = TIC_PROF_NOW();
         // halo: row 32 (17 pixels, corner last) and column 16 (32 pixels) of the region, 8 chunks of 16 B each
         if (e < 49 * 8 && !(TIC_DBG_BITS(p2.dbg) & 4)) {
-          const int hx = e >> 3, ch = e & 7;              // ch 0..3: hi plane, 4..7: lo' plane
+          // consecutive lanes take consecutive halo pixels of one chunk: the caches are chunk-major ([chunk][pixel][16 B])
+          const int ch = e / 49, hx = e - ch * 49;        // ch 0..3: hi plane, 4..7: lo' plane
           uint4 val = make_uint4(0u, 0u, 0u, 0u);
           uint32_t dst;
           if (hx < 17) {                                  // region row 32, column hx (corner hx = 16: the tile below-right)
-            if (has_below && (hx < 16 || has_right)) val = lds128(rowc_rd + (uint32_t)((tx * 16 + hx) * 128 + ch * 16));
+            if (has_below && (hx < 16 || has_right)) val = lds128(rowc_rd + (uint32_t)((ch * rowc_px + tx * 16 + hx) * 16));
             dst = cell(32, hx);
           } else {                                        // region column 16, row hx - 17
-            if (has_right) val = lds128(colc_rd + (uint32_t)((hx - 17) * 128 + ch * 16));
+            if (has_right) val = lds128(colc_rd + (uint32_t)((ch * 32 + hx - 17) * 16));
             dst = cell(hx - 17, 16);
           }
           const uint32_t addr = (ch < 4 ? reg_hi : reg_lo) + dst + (uint32_t)(ch & 3) * 16u;
@@ -496,18 +498,18 @@ fused_enc_kernel(const __grid_constant__ CUtensorMap tm_img, const __grid_consta
           sts128(fused_swz128(al), lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
           sts128(fused_swz128(al + 16u), lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
           if (R == 0) {    // first row of the region: halo row of the tile above (corner of the tile above-left)
-            const uint32_t c0 = rowc_wr + (uint32_t)((tx * 16 + C) * 128 + ci * 32);
+            const uint32_t c0 = rowc_wr + (uint32_t)((2 * ci * rowc_px + tx * 16 + C) * 16), cs = (uint32_t)rowc_px * 16u;
             sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
-            sts128(c0 + 16u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
-            sts128(c0 + 64u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
-            sts128(c0 + 80u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+            sts128(c0 + cs, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+            sts128(c0 + 4u * cs, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+            sts128(c0 + 5u * cs, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
           }
           if (C == 0) {    // first column: halo column of the tile to the left
-            const uint32_t c0 = colc_wr + (uint32_t)(R * 128 + ci * 32);
+            const uint32_t c0 = colc_wr + (uint32_t)((2 * ci * 32 + R) * 16);
             sts128(c0, hp[ci][0], hp[ci][1], hp[ci][2], hp[ci][3]);
-            sts128(c0 + 16u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
-            sts128(c0 + 64u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
-            sts128(c0 + 80u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
+            sts128(c0 + 512u, hp[ci][4], hp[ci][5], hp[ci][6], hp[ci][7]);
+            sts128(c0 + 2048u, lp[ci][0], lp[ci][1], lp[ci][2], lp[ci][3]);
+            sts128(c0 + 2560u, lp[ci][4], lp[ci][5], lp[ci][6], lp[ci][7]);
           }
         }
         ptx::fence_proxy_async_smem();

@@ -1,10 +1,10 @@
 #!/usr/bin/env python
-"""Summarise `nvcc -Xptxas -v` output: kernel, registers, stack, spills (tools/ptxas_table.py < log)."""
+"""Summarise `nvcc -Xptxas -v` output: kernel, registers, stack, spills (tools/ptxas_table.py [log], default stdin)."""
 import re
 import subprocess
 import sys
 
-txt = sys.stdin.read()
+txt = open(sys.argv[1], errors="replace").read() if len(sys.argv) > 1 else sys.stdin.read()
 cur = None
 rows = []
 for ln in txt.splitlines():

@@ -15,9 +15,10 @@
 // the first row / first column of every tile is kept in small shared-memory caches for the tile above / to the left
 // (zeros at the patch border = the conv's zero padding), so MMA1 does exactly the work of the unfused layer.
 //
-// Warps (832 threads, <= 78 registers): 0 raw-window TMA, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue
+// Warps (768 threads, 80 registers): 0 raw-window TMA, 1 MMA issuer (leader CTA), 2 TMEM allocator, 4-19 epilogue
 // (four per TMEM lane quadrant: one first-layer sub-tile each, and an eight-channel share of epilogue 2 one tile
-// behind), 20-25 builders.  TMEM: 4 x 64 columns for MMA1's sub-tiles, two buffers of 64 columns for MMA2.
+// behind), 20-23 builders (four: with the integer operand they are never late, and two warps fewer leave the epilogue warps
+// 80 instead of 72 registers: 1.77 -> 1.70 ms; three builders: 1.77).  TMEM: 4 x 64 columns for MMA1's sub-tiles, two buffers of 64 columns for MMA2.
 // Waiting: one warp of a group polls an mbarrier and releases the others through a named barrier, and a group's
 // arrivals are gathered by a named barrier into one mbarrier arrival per CTA — a warp parked in `mbarrier.try_wait`
 // is woken by every mbarrier event of the CTA and re-polls (7 instructions): with every warp polling and arriving for
@@ -28,8 +29,8 @@
 
 namespace tic {
 
-constexpr int kFEThreads = 832;
-constexpr int kFEBuilderWarp0 = 20, kFEBuilders = 6;
+constexpr int kFEThreads = 768;
+constexpr int kFEBuilderWarp0 = 20, kFEBuilders = 4;
 constexpr int kFEOpCols = 34;                                   // input pixels per operand row: 2 * 16 + 1 halo + 1 over-read
 constexpr uint32_t kFEOpPitch = kFEOpCols * 8;                  // 272 bytes (RGB0 fp16 quads)
 constexpr int kFEOpRows = 65;                                   // 2 * 32 + 1
